@@ -1,0 +1,48 @@
+"""Builds libehic_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels with the
+working tree.  Invoked by ``__graft_entry__.build()`` and lazily by :mod:`._lib` when the
+library is missing or older than its sources.
+"""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libehic_b200.so")
+SOURCES = ["ehic_b200.cu", "kernels.cuh", "layout.hpp"]
+HEADER = os.path.join(os.path.dirname(HERE), "include", "ehic_b200.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [HEADER]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def nvcc_path():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def build(force=False, verbose=False):
+    """Compile the library if needed; returns its path."""
+    if not force and not _stale():
+        return LIB
+    nvcc = nvcc_path()
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libehic_b200.so (there is no CPU fallback)")
+    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, "ehic_b200.cu"), "-o", LIB]
+    if verbose:
+        print("[ensemble_hic_b200]", " ".join(cmd))
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

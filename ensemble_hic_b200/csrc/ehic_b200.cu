@@ -1,0 +1,577 @@
+// ehic_b200.cu -- C ABI (include/ehic_b200.h) over the sm_100a kernels in kernels.cuh.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// There is deliberately no CPU implementation behind these entry points: without a
+// compute-capability-10 device every compute call fails with EHIC_ERR_NODEVICE.
+#include "../../include/ehic_b200.h"
+#include "kernels.cuh"
+#include "layout.hpp"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+using namespace ehic;
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(e_ == cudaErrorMemoryAllocation ? EHIC_ERR_NOMEM : EHIC_ERR_CUDA,  \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));               \
+    } while (0)
+
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+struct ehic_model {
+    int device = 0;
+    int flags = 0;
+    int max_replicas = 0;
+    DevModel dm{};
+    ContactLayout layout;           // host copy (sizes, perm)
+    std::vector<void *> owned;      // device allocations
+    // workspace
+    double *xs[2] = {nullptr, nullptr};
+    double *wbuf = nullptr, *partA = nullptr, *partB = nullptr;
+    double *energies = nullptr, *kinetic = nullptr;
+    int nA = 0;                     // forward blocks per replica
+    int kt = 1, nkt = 1;
+    // staging for the host entry points
+    double *st_x = nullptr, *st_g = nullptr, *st_md = nullptr, *st_small = nullptr;
+    cudaStream_t st_stream = nullptr;
+};
+
+template <typename T>
+static int upload(ehic_model *m, const std::vector<T> &v, const T **out)
+{
+    T *d = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CU(cudaMalloc(&d, bytes));
+    m->owned.push_back(d);
+    if (!v.empty()) CU(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = d;
+    return EHIC_OK;
+}
+
+static int dalloc(ehic_model *m, double **out, size_t n)
+{
+    double *d = nullptr;
+    CU(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(double)));
+    m->owned.push_back(d);
+    *out = d;
+    return EHIC_OK;
+}
+
+extern "C" {
+
+int ehic_version(void) { return 100; }
+const char *ehic_last_error(void) { return g_err.c_str(); }
+int64_t ehic_launch_count(void) { return g_launches.load(); }
+
+int ehic_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+static int check_device(int device)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(EHIC_ERR_NODEVICE, "no CUDA device visible: libehic_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(EHIC_ERR_INVALID, "device index out of range");
+    int major = 0;
+    CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10)
+        return fail(EHIC_ERR_NODEVICE, "device is not compute capability 10.x (kernels are built for sm_100a only)");
+    return EHIC_OK;
+}
+
+static int pick_kt(int S)
+{
+    const char *env = getenv("EHIC_KT");
+    if (env) { int v = atoi(env); if (v == 1 || v == 2 || v == 4) return v; }
+    if (S >= 4) return 4;
+    if (S >= 2) return 2;
+    return 1;
+}
+
+int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **out)
+{
+    if (!desc || !out) return fail(EHIC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (desc->n_beads <= 0 || desc->n_structures <= 0) return fail(EHIC_ERR_INVALID, "n_beads and n_structures must be positive");
+    if (desc->n_data < 0 || (desc->n_data > 0 && (!desc->data_points || !desc->contact_distances)))
+        return fail(EHIC_ERR_INVALID, "data_points / contact_distances missing");
+    if (!desc->bead_radii) return fail(EHIC_ERR_INVALID, "bead_radii missing");
+    if (desc->max_replicas <= 0) return fail(EHIC_ERR_INVALID, "max_replicas must be positive");
+    if (desc->flags & (EHIC_FLAG_FP32 | EHIC_FLAG_NB_CELLS))
+        return fail(EHIC_ERR_INVALID, "EHIC_FLAG_FP32 / EHIC_FLAG_NB_CELLS are not available in this build");
+    int rc = check_device(device);
+    if (rc) return rc;
+    CU(cudaSetDevice(device));
+
+    ehic_model *m = new (std::nothrow) ehic_model();
+    if (!m) return fail(EHIC_ERR_NOMEM, "host allocation failed");
+    m->device = device; m->flags = desc->flags; m->max_replicas = desc->max_replicas;
+    const int N = desc->n_beads, S = desc->n_structures;
+    const bool exact = (desc->flags & EHIC_FLAG_EXACT) != 0;
+    std::string err = build_layout(N, desc->n_data, desc->data_points, desc->contact_distances, exact, m->layout);
+    if (!err.empty()) { delete m; return fail(EHIC_ERR_INVALID, err); }
+    ContactLayout &L = m->layout;
+
+    // bonds: [N] arrays indexed by bond (b, b+1)
+    std::vector<double> ul(N, std::numeric_limits<double>::infinity()), ll(N, 0.0);
+    std::vector<char> is_end(N, 0);
+    if (desc->mol_ranges && desc->n_mol_ranges >= 2) {
+        if (desc->mol_ranges[0] != 0 || desc->mol_ranges[desc->n_mol_ranges - 1] != N) {
+            delete m; return fail(EHIC_ERR_INVALID, "mol_ranges must start at 0 and end at n_beads");
+        }
+        for (int q = 1; q < desc->n_mol_ranges; q++) {
+            if (desc->mol_ranges[q] <= desc->mol_ranges[q - 1]) { delete m; return fail(EHIC_ERR_INVALID, "mol_ranges must be increasing"); }
+            is_end[desc->mol_ranges[q] - 1] = 1;
+        }
+    } else {
+        is_end[N - 1] = 1;
+    }
+    for (int b = 0; b + 1 < N; b++) {
+        if (is_end[b]) continue;
+        ul[b] = desc->bb_upper ? desc->bb_upper[b] : desc->bead_radii[b] + desc->bead_radii[b + 1];
+        ll[b] = desc->bb_lower ? desc->bb_lower[b] : 0.0;
+    }
+    std::vector<double> radii(desc->bead_radii, desc->bead_radii + N);
+
+    DevModel &dm = m->dm;
+    dm.N = N; dm.S = S; dm.Np = (N + 31) / 32 * 32; dm.n_slices = L.n_slices;
+    dm.M = L.M; dm.tot = L.tot;
+    dm.alpha = desc->alpha; dm.k_nb = desc->nonbonded_k; dm.k_bb = desc->backbone_k;
+    dm.sphere_active = desc->sphere_active;
+    dm.sph_R = desc->sphere_radius; dm.sph_k = desc->sphere_k;
+    dm.sph_cx = desc->sphere_center[0]; dm.sph_cy = desc->sphere_center[1]; dm.sph_cz = desc->sphere_center[2];
+
+    std::vector<long long> perm(L.perm.begin(), L.perm.end()), soff(L.slice_off.begin(), L.slice_off.end());
+#define UP(vec, field)                                              \
+    do { rc = upload(m, vec, &dm.field); if (rc) { ehic_model_destroy(m); return rc; } } while (0)
+    UP(L.pi, pi); UP(L.pj, pj); UP(L.slot_a, slot_a); UP(L.slot_b, slot_b);
+    UP(L.pdc, pdc); UP(L.pcnt, pcnt); UP(perm, perm);
+    UP(soff, slice_off); UP(L.slice_w, slice_w); UP(L.ent_j, ent_j); UP(L.ent_dc, ent_dc);
+    UP(radii, radii); UP(ul, bb_ul); UP(ll, bb_ll);
+#undef UP
+    // free the big host vectors we no longer need
+    std::vector<int32_t>().swap(L.ent_j); std::vector<double>().swap(L.ent_dc);
+    std::vector<int32_t>().swap(L.slot_a); std::vector<int32_t>().swap(L.slot_b);
+    std::vector<double>().swap(L.pdc); std::vector<double>().swap(L.pcnt);
+
+    m->kt = pick_kt(S);
+    m->nkt = (S + m->kt - 1) / m->kt;
+    m->nA = (int)((L.M + 255) / 256);
+    const size_t Rm = (size_t)desc->max_replicas;
+    const size_t xs_n = Rm * S * 3 * (size_t)dm.Np;
+#define DA(ptr, n)                                                   \
+    do { rc = dalloc(m, &(ptr), (n)); if (rc) { ehic_model_destroy(m); return rc; } } while (0)
+    DA(m->xs[0], xs_n); DA(m->xs[1], xs_n);
+    DA(m->wbuf, Rm * (size_t)L.tot);
+    DA(m->partA, Rm * (size_t)std::max(m->nA, 1));
+    DA(m->partB, Rm * (size_t)L.n_slices * m->nkt * 4);
+    DA(m->energies, Rm * 4); DA(m->kinetic, Rm);
+#undef DA
+    // weights of padding slots are never read (ent_j < 0), but keep the buffer defined
+    if (cudaMemset(m->wbuf, 0, std::max<size_t>(Rm * (size_t)L.tot, 1) * sizeof(double)) != cudaSuccess) {
+        ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed");
+    }
+    if (cudaStreamCreateWithFlags(&m->st_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    *out = m;
+    return EHIC_OK;
+}
+
+int ehic_model_destroy(ehic_model_t *m)
+{
+    if (!m) return EHIC_OK;
+    cudaSetDevice(m->device);
+    for (void *p : m->owned) cudaFree(p);
+    cudaFree(m->st_x); cudaFree(m->st_g); cudaFree(m->st_md); cudaFree(m->st_small);
+    if (m->st_stream) cudaStreamDestroy(m->st_stream);
+    delete m;
+    return EHIC_OK;
+}
+
+int ehic_model_set_param(ehic_model_t *m, int which, double v)
+{
+    if (!m) return fail(EHIC_ERR_INVALID, "null model");
+    switch (which) {
+    case EHIC_PARAM_ALPHA: m->dm.alpha = v; break;
+    case EHIC_PARAM_NONBONDED_K: m->dm.k_nb = v; break;
+    case EHIC_PARAM_BACKBONE_K: m->dm.k_bb = v; break;
+    case EHIC_PARAM_SPHERE_RADIUS: m->dm.sph_R = v; break;
+    case EHIC_PARAM_SPHERE_K: m->dm.sph_k = v; break;
+    case EHIC_PARAM_SPHERE_CX: m->dm.sph_cx = v; break;
+    case EHIC_PARAM_SPHERE_CY: m->dm.sph_cy = v; break;
+    case EHIC_PARAM_SPHERE_CZ: m->dm.sph_cz = v; break;
+    default: return fail(EHIC_ERR_INVALID, "unknown parameter id");
+    }
+    return EHIC_OK;
+}
+
+int ehic_model_get_param(const ehic_model_t *m, int which, double *v)
+{
+    if (!m || !v) return fail(EHIC_ERR_INVALID, "null argument");
+    switch (which) {
+    case EHIC_PARAM_ALPHA: *v = m->dm.alpha; break;
+    case EHIC_PARAM_NONBONDED_K: *v = m->dm.k_nb; break;
+    case EHIC_PARAM_BACKBONE_K: *v = m->dm.k_bb; break;
+    case EHIC_PARAM_SPHERE_RADIUS: *v = m->dm.sph_R; break;
+    case EHIC_PARAM_SPHERE_K: *v = m->dm.sph_k; break;
+    case EHIC_PARAM_SPHERE_CX: *v = m->dm.sph_cx; break;
+    case EHIC_PARAM_SPHERE_CY: *v = m->dm.sph_cy; break;
+    case EHIC_PARAM_SPHERE_CZ: *v = m->dm.sph_cz; break;
+    default: return fail(EHIC_ERR_INVALID, "unknown parameter id");
+    }
+    return EHIC_OK;
+}
+
+int ehic_model_info(const ehic_model_t *m, int64_t out[8])
+{
+    if (!m || !out) return fail(EHIC_ERR_INVALID, "null argument");
+    out[0] = m->dm.N; out[1] = m->dm.S; out[2] = m->dm.M; out[3] = m->max_replicas;
+    out[4] = m->flags; out[5] = m->dm.tot; out[6] = m->device; out[7] = m->kt;
+    return EHIC_OK;
+}
+
+}  // extern "C"
+
+// ---- internal launch helpers ------------------------------------------------------------
+
+static int check_call(ehic_model *m, int R)
+{
+    if (!m) return fail(EHIC_ERR_INVALID, "null model");
+    if (R <= 0 || R > m->max_replicas) return fail(EHIC_ERR_INVALID, "R must be in [1, max_replicas]");
+    CU(cudaSetDevice(m->device));
+    return EHIC_OK;
+}
+
+static int launch_pack(ehic_model *m, int R, const double *d_x, double *xs, cudaStream_t st)
+{
+    long long rows = (long long)R * m->dm.S, total = rows * m->dm.Np;
+    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_x, xs, m->dm.N, m->dm.Np, rows);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return EHIC_OK;
+}
+
+static int launch_forward(ehic_model *m, int R, const double *xs, const double *d_norm, double *d_md,
+                          bool want_w, bool want_logl, cudaStream_t st)
+{
+    if (m->dm.M == 0) {
+        if (want_logl) CU(cudaMemsetAsync(m->partA, 0, sizeof(double) * (size_t)R * std::max(m->nA, 1), st));
+        return EHIC_OK;
+    }
+    dim3 grid((unsigned)m->nA, (unsigned)R);
+    if (m->flags & EHIC_FLAG_EXACT)
+        forward_kernel<true><<<grid, 256, 0, st>>>(m->dm, xs, d_norm, d_md, want_w ? m->wbuf : nullptr, m->partA, want_logl);
+    else
+        forward_kernel<false><<<grid, 256, 0, st>>>(m->dm, xs, d_norm, d_md, want_w ? m->wbuf : nullptr, m->partA, want_logl);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return EHIC_OK;
+}
+
+template <bool EXACT>
+static void launch_gather_t(ehic_model *m, const GatherArgs &ga, int R, cudaStream_t st)
+{
+    long long items = (long long)R * m->dm.n_slices * m->nkt;
+    unsigned blocks = (unsigned)((items + 3) / 4);
+    switch (m->kt) {
+    case 4: gather_kernel<EXACT, 4><<<blocks, 128, 0, st>>>(m->dm, ga, R, m->nkt); break;
+    case 2: gather_kernel<EXACT, 2><<<blocks, 128, 0, st>>>(m->dm, ga, R, m->nkt); break;
+    default: gather_kernel<EXACT, 1><<<blocks, 128, 0, st>>>(m->dm, ga, R, m->nkt); break;
+    }
+    LAUNCHED();
+}
+
+static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_t st)
+{
+    if (m->flags & EHIC_FLAG_EXACT) launch_gather_t<true>(m, ga, R, st);
+    else launch_gather_t<false>(m, ga, R, st);
+    CU(cudaGetLastError());
+    return EHIC_OK;
+}
+
+static int launch_finalize(ehic_model *m, int R, bool haveA, bool haveB, double *d_energies, double *d_kin, cudaStream_t st)
+{
+    finalize_kernel<<<R, 256, 0, st>>>(m->dm, haveA ? m->partA : nullptr, m->nA, haveB ? m->partB : nullptr,
+                                       (long long)m->dm.n_slices * m->nkt, d_energies, d_kin);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return EHIC_OK;
+}
+
+extern "C" {
+
+// ---- hot path, device buffers -----------------------------------------------------------
+
+int ehic_mock_data(ehic_model_t *m, int R, const double *d_x, const double *d_norm, double *d_md, void *stream)
+{
+    int rc = check_call(m, R);
+    if (rc) return rc;
+    if (!d_x || !d_norm || !d_md) return fail(EHIC_ERR_INVALID, "null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_pack(m, R, d_x, m->xs[0], st);
+    if (rc) return rc;
+    return launch_forward(m, R, m->xs[0], d_norm, d_md, false, false, st);
+}
+
+int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const double *d_norm,
+                  const double *d_lammda, const double *d_beta,
+                  double *d_grad, double *d_energies, double *d_md, void *stream)
+{
+    int rc = check_call(m, R);
+    if (rc) return rc;
+    if (!d_x) return fail(EHIC_ERR_INVALID, "null coordinates");
+    terms &= EHIC_TERM_ALL;
+    if (!m->dm.sphere_active) terms &= ~EHIC_TERM_SPHERE;
+    const bool lik = (terms & EHIC_TERM_LIKELIHOOD) != 0;
+    if ((lik || d_md) && !d_norm) return fail(EHIC_ERR_INVALID, "norm required for the likelihood term");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_pack(m, R, d_x, m->xs[0], st);
+    if (rc) return rc;
+    const bool need_forward = (lik && (d_grad || d_energies)) || d_md;
+    if (need_forward) {
+        rc = launch_forward(m, R, m->xs[0], d_norm, d_md, lik && d_grad, lik && d_energies, st);
+        if (rc) return rc;
+    }
+    const bool need_gather = d_grad || (d_energies && (terms & ~EHIC_TERM_LIKELIHOOD));
+    if (need_gather) {
+        GatherArgs ga{};
+        ga.xs = m->xs[0]; ga.wbuf = m->wbuf; ga.lammda = d_lammda; ga.beta = d_beta;
+        ga.grad = d_grad; ga.partB = d_energies ? m->partB : nullptr; ga.terms = terms;
+        rc = launch_gather(m, ga, R, st);
+        if (rc) return rc;
+    }
+    if (d_energies) {
+        rc = launch_finalize(m, R, lik && need_forward, need_gather, d_energies, nullptr, st);
+        if (rc) return rc;
+    }
+    return EHIC_OK;
+}
+
+int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double *d_p,
+                        const double *d_norm, const double *d_lammda, const double *d_beta,
+                        const double *d_eps, double *d_H, void *stream)
+{
+    int rc = check_call(m, R);
+    if (rc) return rc;
+    if (!d_x || !d_p || !d_norm || !d_eps || !d_H) return fail(EHIC_ERR_INVALID, "null buffer");
+    if (n_steps < 1) return fail(EHIC_ERR_INVALID, "n_steps must be >= 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    int terms = EHIC_TERM_ALL;
+    if (!m->dm.sphere_active) terms &= ~EHIC_TERM_SPHERE;
+    rc = launch_pack(m, R, d_x, m->xs[0], st);
+    if (rc) return rc;
+    int cur = 0;
+    for (int s = 0; s <= n_steps; s++) {
+        const bool first = (s == 0), last = (s == n_steps);
+        const bool ends = first || last;
+        rc = launch_forward(m, R, m->xs[cur], d_norm, nullptr, true, ends, st);
+        if (rc) return rc;
+        GatherArgs ga{};
+        ga.xs = m->xs[cur]; ga.wbuf = m->wbuf; ga.lammda = d_lammda; ga.beta = d_beta;
+        ga.grad = nullptr; ga.partB = ends ? m->partB : nullptr; ga.terms = terms;
+        ga.p = d_p; ga.eps = d_eps; ga.kick = ends ? 0.5 : 1.0;
+        ga.xs_next = last ? nullptr : m->xs[cur ^ 1];
+        ga.kinetic_before = first ? 1 : (last ? 2 : 0);
+        rc = launch_gather(m, ga, R, st);
+        if (rc) return rc;
+        if (ends) {
+            rc = launch_finalize(m, R, true, true, m->energies, m->kinetic, st);
+            if (rc) return rc;
+            hamiltonian_kernel<<<(R + 127) / 128, 128, 0, st>>>(m->energies, m->kinetic, d_lammda, d_beta, d_H, first ? 0 : 2, R);
+            LAUNCHED();
+            CU(cudaGetLastError());
+        }
+        if (!last) cur ^= 1;
+    }
+    long long rows = (long long)R * m->dm.S, total = rows * m->dm.N;
+    unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m->xs[cur], d_x, m->dm.N, m->dm.Np, rows);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return EHIC_OK;
+}
+
+int ehic_select(int R, int64_t n, const int32_t *d_mask, const double *d_src, double *d_dst, void *stream)
+{
+    if (R <= 0 || n <= 0 || !d_mask || !d_src || !d_dst) return fail(EHIC_ERR_INVALID, "bad argument");
+    long long total = (long long)R * n;
+    select_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(R, n, d_mask, d_src, d_dst);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return EHIC_OK;
+}
+
+// ---- neighbour list -----------------------------------------------------------------------
+
+int ehic_nblist_host(int n_beads, const double *h_coords, double cutoff,
+                     int32_t *h_pairs, int64_t capacity, int64_t *n_pairs, int device)
+{
+    if (n_beads <= 0 || !h_coords || !n_pairs || capacity < 0 || (capacity > 0 && !h_pairs))
+        return fail(EHIC_ERR_INVALID, "bad argument");
+    int rc = check_device(device);
+    if (rc) return rc;
+    CU(cudaSetDevice(device));
+    const int N = n_beads;
+    double *d_x = nullptr; int *d_cnt = nullptr; long long *d_off = nullptr; int *d_pairs = nullptr;
+    int status = EHIC_OK;
+    std::vector<int> cnt(N);
+    std::vector<long long> off(N + 1, 0);
+    const double cut2 = cutoff * cutoff;      // nblist.c:198 cellsize2 = cellsize * cellsize
+    do {
+#define CUB(call) if ((call) != cudaSuccess) { status = fail(EHIC_ERR_CUDA, #call " failed"); break; }
+        CUB(cudaMalloc(&d_x, sizeof(double) * 3 * N));
+        CUB(cudaMalloc(&d_cnt, sizeof(int) * N));
+        CUB(cudaMalloc(&d_off, sizeof(long long) * N));
+        CUB(cudaMemcpy(d_x, h_coords, sizeof(double) * 3 * N, cudaMemcpyHostToDevice));
+        nblist_count_kernel<<<(N + 127) / 128, 128>>>(d_x, N, cut2, d_cnt);
+        LAUNCHED();
+        CUB(cudaMemcpy(cnt.data(), d_cnt, sizeof(int) * N, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < N; i++) off[i + 1] = off[i] + cnt[i];
+        *n_pairs = off[N];
+        long long cap = std::min<long long>(capacity, off[N]);
+        if (cap > 0) {
+            CUB(cudaMalloc(&d_pairs, sizeof(int) * 2 * cap));
+            CUB(cudaMemcpy(d_off, off.data(), sizeof(long long) * N, cudaMemcpyHostToDevice));
+            nblist_fill_kernel<<<(N + 127) / 128, 128>>>(d_x, N, cut2, d_off, d_pairs, cap);
+            LAUNCHED();
+            CUB(cudaMemcpy(h_pairs, d_pairs, sizeof(int) * 2 * cap, cudaMemcpyDeviceToHost));
+        }
+        if (off[N] > capacity && capacity > 0) status = fail(EHIC_ERR_CAPACITY, "pair buffer too small");
+#undef CUB
+    } while (0);
+    cudaFree(d_x); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_pairs);
+    return status;
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------
+
+static int ensure_staging(ehic_model *m)
+{
+    if (m->st_x) return EHIC_OK;
+    const size_t Rm = (size_t)m->max_replicas;
+    const size_t nx = Rm * m->dm.S * (size_t)m->dm.N * 3;
+    CU(cudaMalloc(&m->st_x, sizeof(double) * nx));
+    CU(cudaMalloc(&m->st_g, sizeof(double) * nx));
+    CU(cudaMalloc(&m->st_md, sizeof(double) * std::max<size_t>(Rm * (size_t)m->dm.M, 1)));
+    CU(cudaMalloc(&m->st_small, sizeof(double) * Rm * 8));
+    return EHIC_OK;
+}
+
+int ehic_mock_data_host(ehic_model_t *m, int R, const double *h_x, const double *h_norm, double *h_md)
+{
+    return ehic_evaluate_host(m, R, 0, h_x, h_norm, nullptr, nullptr, nullptr, nullptr, h_md);
+}
+
+int ehic_evaluate_host(ehic_model_t *m, int R, int terms, const double *h_x, const double *h_norm,
+                       const double *h_lammda, const double *h_beta,
+                       double *h_grad, double *h_energies, double *h_md)
+{
+    int rc = check_call(m, R);
+    if (rc) return rc;
+    if (!h_x) return fail(EHIC_ERR_INVALID, "null coordinates");
+    rc = ensure_staging(m);
+    if (rc) return rc;
+    cudaStream_t st = m->st_stream;
+    const size_t nx = (size_t)R * m->dm.S * (size_t)m->dm.N * 3;
+    double *d_norm = m->st_small, *d_lam = m->st_small + m->max_replicas, *d_bet = m->st_small + 2 * (size_t)m->max_replicas;
+    double *d_E = m->st_small + 3 * (size_t)m->max_replicas;   // 4 * Rmax
+    CU(cudaMemcpyAsync(m->st_x, h_x, sizeof(double) * nx, cudaMemcpyHostToDevice, st));
+    if (h_norm) CU(cudaMemcpyAsync(d_norm, h_norm, sizeof(double) * R, cudaMemcpyHostToDevice, st));
+    if (h_lammda) CU(cudaMemcpyAsync(d_lam, h_lammda, sizeof(double) * R, cudaMemcpyHostToDevice, st));
+    if (h_beta) CU(cudaMemcpyAsync(d_bet, h_beta, sizeof(double) * R, cudaMemcpyHostToDevice, st));
+    rc = ehic_evaluate(m, R, terms, m->st_x, h_norm ? d_norm : nullptr, h_lammda ? d_lam : nullptr,
+                       h_beta ? d_bet : nullptr, h_grad ? m->st_g : nullptr, h_energies ? d_E : nullptr,
+                       h_md ? m->st_md : nullptr, st);
+    if (rc) return rc;
+    if (h_grad) CU(cudaMemcpyAsync(h_grad, m->st_g, sizeof(double) * nx, cudaMemcpyDeviceToHost, st));
+    if (h_energies) CU(cudaMemcpyAsync(h_energies, d_E, sizeof(double) * 4 * R, cudaMemcpyDeviceToHost, st));
+    if (h_md && m->dm.M > 0) CU(cudaMemcpyAsync(h_md, m->st_md, sizeof(double) * (size_t)R * m->dm.M, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return EHIC_OK;
+}
+
+// ---- layout debug (host only) ----------------------------------------------------------------
+
+int ehic_layout_debug(int32_t n_beads, int64_t n_data, const int64_t *data_points, int exact_order,
+                      int64_t *h_sorted, int64_t *n_slots, int32_t *h_row_len)
+{
+    if (n_data > 0 && !data_points) return fail(EHIC_ERR_INVALID, "null data_points");
+    ContactLayout L;
+    std::string err = build_layout(n_beads, n_data, data_points, nullptr, exact_order != 0, L, false);
+    if (!err.empty()) return fail(EHIC_ERR_INVALID, err);
+    if (h_sorted) for (int64_t s = 0; s < n_data; s++) h_sorted[s] = L.perm[s];
+    if (n_slots) *n_slots = L.tot;
+    if (h_row_len) for (int32_t b = 0; b < n_beads; b++) h_row_len[b] = L.row_len[b];
+    // self-check of the row view: every sorted pair must be found at its two slots
+    for (int64_t s = 0; s < n_data; s++) {
+        if (L.ent_j[L.slot_a[s]] != L.pj[s] || L.ent_j[L.slot_b[s]] != L.pi[s])
+            return fail(EHIC_ERR_INVALID, "internal: row view inconsistent");
+    }
+    return EHIC_OK;
+}
+
+// ---- measurement helpers -----------------------------------------------------------------------
+
+int ehic_fma_peak(int device, int fp64, int iters, double *tflops, double *ms_per_launch)
+{
+    if (!tflops) return fail(EHIC_ERR_INVALID, "null output");
+    int rc = check_device(device);
+    if (rc) return rc;
+    CU(cudaSetDevice(device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sms * 8, threads = 256, inner = 4096;
+    void *buf = nullptr;
+    CU(cudaMalloc(&buf, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    if (iters < 1) iters = 1;
+    for (int w = 0; w < 2; w++) {
+        if (fp64) fma_peak_kernel<double><<<blocks, threads>>>((double *)buf, inner, 1.0000001, 1e-9);
+        else fma_peak_kernel<float><<<blocks, threads>>>((float *)buf, inner, 1.0000001f, 1e-9f);
+        LAUNCHED();
+    }
+    CU(cudaEventRecord(e0));
+    for (int w = 0; w < iters; w++) {
+        if (fp64) fma_peak_kernel<double><<<blocks, threads>>>((double *)buf, inner, 1.0000001, 1e-9);
+        else fma_peak_kernel<float><<<blocks, threads>>>((float *)buf, inner, 1.0000001f, 1e-9f);
+        LAUNCHED();
+    }
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    double flops = 2.0 * 64.0 * inner * (double)blocks * threads * iters;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    if (ms_per_launch) *ms_per_launch = ms / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    return EHIC_OK;
+}
+
+}  // extern "C"

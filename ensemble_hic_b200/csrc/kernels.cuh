@@ -1,0 +1,584 @@
+// kernels.cuh -- sm_100a kernels of the ensemble_hic posterior hot path.
+//
+// Not a dense contraction: no tensor cores.  The large configurations are bound by the
+// FP64 pipe (64 DFMA lanes / clk / SM), the small ones by launch latency; see DESIGN.md.
+//
+// Working layout of the coordinates inside the kernels ("xs"): [R][S][3][Np] FP64, SoA per
+// structure, Np = N rounded up to 32.  A warp whose lanes are consecutive beads of one
+// structure then reads 256 contiguous bytes per component, and a warp that gathers the
+// (nearly identical) partner index reads one or two sectors.  The public layout
+// [R][S][N][3] (forward_models.py:78) is converted by pack_kernel (4.8 MB per replica at
+// N=2000, S=100: noise next to the pair arithmetic).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ehic {
+
+struct DevModel {
+    int N, S, Np, n_slices;
+    long long M, tot;
+    // pair view
+    const int *pi, *pj, *slot_a, *slot_b;
+    const double *pdc, *pcnt;
+    const long long *perm;
+    // row view
+    const long long *slice_off;
+    const int *slice_w;
+    const int *ent_j;
+    const double *ent_dc;
+    // per bead
+    const double *radii;    // [N]
+    const double *bb_ul;    // [N] upper limit of bond (b, b+1); +inf where there is no bond
+    const double *bb_ll;    // [N] lower limit of bond (b, b+1); 0    where there is no bond
+    double alpha, k_nb, k_bb, sph_R, sph_k, sph_cx, sph_cy, sph_cz;
+    int sphere_active;
+};
+
+// ---------------------------------------------------------------------------------------
+// arithmetic helpers
+
+// Full-precision 1/sqrt(x) for normal x > 0: MUFU.RSQ64H seed (~2^-22) + one third-order
+// step (error ~ (5/16) e^3 < 2^-60).  5 FP64 instructions, no slow path; x = 0 gives inf/NaN
+// exactly where the reference divides by zero.
+__device__ __forceinline__ double rsqrt_nr(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    double a = x * y0;
+    double e = fma(-a, y0, 1.0);
+    double p = fma(0.375, e, 0.5);
+    double ye = y0 * e;
+    return fma(ye, p, y0);
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{   // fixed butterfly order: deterministic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// x[R][S][N][3] -> xs[R][S][3][Np]
+__global__ void pack_kernel(const double *__restrict__ x, double *__restrict__ xs,
+                            int N, int Np, long long rows /* R*S */)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = rows * Np;
+    if (t >= total) return;
+    long long row = t / Np;
+    int i = (int)(t - row * Np);
+    double a = 0.0, b = 0.0, c = 0.0;
+    if (i < N) {
+        const double *p = x + (row * N + i) * 3;
+        a = p[0]; b = p[1]; c = p[2];
+    }
+    double *q = xs + row * 3 * (long long)Np + i;
+    q[0] = a; q[Np] = b; q[2 * (long long)Np] = c;
+}
+
+// xs[R][S][3][Np] -> x[R][S][N][3]
+__global__ void unpack_kernel(const double *__restrict__ xs, double *__restrict__ x,
+                              int N, int Np, long long rows)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = rows * N;
+    if (t >= total) return;
+    long long row = t / N;
+    int i = (int)(t - row * N);
+    const double *q = xs + row * 3 * (long long)Np + i;
+    double *p = x + (row * N + i) * 3;
+    p[0] = q[0]; p[1] = q[Np]; p[2] = q[2 * (long long)Np];
+}
+
+// ---------------------------------------------------------------------------------------
+// Forward kernel: mock data md[m] = norm * sum_k s_km (evaluate_FWM_pureC.pxd:29-39), the
+// Poisson weight w_m = 0.5 (1 - c_m/md_m) norm alpha (likelihoods_c.pyx:24-25,69) scattered
+// into both row slots of the pair, and the per-block partial of
+// log L = sum_m (c_m log md_m - md_m) (error_models.py:97).
+//
+// thread <-> pair m of the (i, j)-sorted list; the reduction over the ensemble is a serial
+// loop over k in the reference's own order (deterministic; bit-exact in EXACT mode).
+template <bool EXACT>
+__global__ void __launch_bounds__(256)
+forward_kernel(DevModel dm, const double *__restrict__ xs, const double *__restrict__ norm,
+               double *__restrict__ md_out, double *__restrict__ wbuf,
+               double *__restrict__ partA, int want_logl)
+{
+    const int r = blockIdx.y;
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long plane = 3LL * dm.Np;
+    const double *xr = xs + (long long)r * dm.S * plane;
+    const double nrm = norm[r];
+    double term = 0.0;
+    if (m < dm.M) {
+        const int i = dm.pi[m], j = dm.pj[m];
+        const double dc = dm.pdc[m], c = dm.pcnt[m];
+        const double alpha = dm.alpha;
+        const double *pa = xr + i, *pb = xr + j;
+        double md;
+        if (EXACT) {
+            const double aa = __dmul_rn(alpha, alpha);
+            md = 0.0;
+            for (int k = 0; k < dm.S; k++, pa += plane, pb += plane) {
+                double d0 = __dsub_rn(pa[0], pb[0]);
+                double d1 = __dsub_rn(pa[dm.Np], pb[dm.Np]);
+                double d2 = __dsub_rn(pa[2 * dm.Np], pb[2 * dm.Np]);
+                double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+                double d = __dsqrt_rn(s);
+                double u = __dsub_rn(dc, d);
+                double q = __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(__dmul_rn(aa, u), u)));
+                double v = __dadd_rn(__ddiv_rn(__dmul_rn(alpha, u), q), 1.0);
+                md = __dadd_rn(md, __dmul_rn(__dmul_rn(v, 0.5), nrm));
+            }
+        } else {
+            double acc0 = 0.0, acc1 = 0.0;
+            int k = 0;
+            for (; k + 1 < dm.S; k += 2, pa += 2 * plane, pb += 2 * plane) {
+                double ax = pa[0] - pb[0], ay = pa[dm.Np] - pb[dm.Np], az = pa[2 * dm.Np] - pb[2 * dm.Np];
+                double bx = pa[plane] - pb[plane], by = pa[plane + dm.Np] - pb[plane + dm.Np],
+                       bz = pa[plane + 2 * dm.Np] - pb[plane + 2 * dm.Np];
+                double sa = fma(az, az, fma(ay, ay, ax * ax));
+                double sb = fma(bz, bz, fma(by, by, bx * bx));
+                double ra = rsqrt_nr(sa), rb = rsqrt_nr(sb);
+                double ta = alpha * (dc - sa * ra), tb = alpha * (dc - sb * rb);
+                double qa = rsqrt_nr(fma(ta, ta, 1.0)), qb = rsqrt_nr(fma(tb, tb, 1.0));
+                acc0 += fma(ta, qa, 1.0);
+                acc1 += fma(tb, qb, 1.0);
+            }
+            if (k < dm.S) {
+                double ax = pa[0] - pb[0], ay = pa[dm.Np] - pb[dm.Np], az = pa[2 * dm.Np] - pb[2 * dm.Np];
+                double sa = fma(az, az, fma(ay, ay, ax * ax));
+                double ra = rsqrt_nr(sa);
+                double ta = alpha * (dc - sa * ra);
+                double qa = rsqrt_nr(fma(ta, ta, 1.0));
+                acc0 += fma(ta, qa, 1.0);
+            }
+            md = (acc0 + acc1) * (0.5 * nrm);
+        }
+        if (md_out) md_out[(long long)r * dm.M + dm.perm[m]] = md;
+        // numerator of f in likelihoods_c.pyx:69: ((0.5 * em) * norm) * alpha, em = 1 - c/md
+        double em = __dsub_rn(1.0, __ddiv_rn(c, md));
+        double w = __dmul_rn(__dmul_rn(__dmul_rn(0.5, em), nrm), alpha);
+        if (wbuf) {
+            double *wr = wbuf + (long long)r * dm.tot;
+            wr[dm.slot_a[m]] = w;
+            wr[dm.slot_b[m]] = w;
+        }
+        if (want_logl) term = c * log(md) - md;
+    }
+    if (want_logl) {
+        __shared__ double sh[8];
+        double v = warp_sum(term);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) t += sh[q];
+            partA[(long long)r * gridDim.x + blockIdx.x] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Gather kernel: everything that produces a per-bead quantity.
+//
+// warp <-> (replica r, slice of 32 consecutive beads, tile of KT structures); lane <-> bead.
+//   1. contact term: walk the lane's row of the sliced-ELL row view, for each partner o and
+//      each of the KT structures recompute the pair (cheaper than storing [S][M] scratch as
+//      the reference does) and accumulate g_b += f * (x_o - x_b)       (likelihoods_c.pyx:62-73)
+//   2. nonbonded term: all beads o != b of the same structure, partner index uniform across
+//      the warp (broadcast loads), quartic repulsion                     (forcefield_c.pyx:33-59,
+//                                                                         c/prolsq.c:8-38)
+//   3. backbone (bonds b-1,b and b,b+1) and sphere terms              (backbone_prior_c.pyx:11-44,
+//                                                                         sphere_prior_c.pyx:12-38)
+//   4. epilogue: tempered sum written to grad[R][S][N][3]; optional leapfrog kick + drift
+//      (HMC trajectories keep x, p on the device); per-warp energy partials.
+// No atomics anywhere: every output element has exactly one writer and a fixed summation order.
+
+struct GatherArgs {
+    const double *xs;       // [R][S][3][Np] positions the gradient is evaluated at
+    const double *wbuf;     // [R][tot] per-slot Poisson weights (from forward_kernel)
+    const double *lammda;   // [R] or NULL
+    const double *beta;     // [R] or NULL
+    double *grad;           // [R][S][N][3] or NULL
+    double *partB;          // [items][4] (a^4 sum, backbone E, sphere E, kinetic) or NULL
+    int terms;
+    // leapfrog epilogue (all NULL/0 outside HMC)
+    double *p;              // [R][S][N][3] momenta, updated in place:  p -= kick * eps * g
+    const double *eps;      // [R]
+    double kick;            // 0.5 or 1.0
+    double *xs_next;        // [R][S][3][Np]: xs + eps * p (after the kick), or NULL (no drift)
+    int kinetic_before;     // partB[3] = sum p^2 before the kick (1) / after the kick (2) / none (0)
+};
+
+template <bool EXACT, int KT>
+__global__ void __launch_bounds__(128)
+gather_kernel(DevModel dm, GatherArgs ga, int R, int nkt)
+{
+    const int lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long n_items = (long long)R * dm.n_slices * nkt;
+    if (item >= n_items) return;
+    const int kt = (int)(item % nkt);
+    const long long tmp = item / nkt;
+    const int sl = (int)(tmp % dm.n_slices);
+    const int r = (int)(tmp / dm.n_slices);
+    const int b = sl * 32 + lane;
+    const bool bead_ok = b < dm.N;
+    const int bb = bead_ok ? b : dm.N - 1;           // clamped index for loads
+    const int Np = dm.Np;
+    const long long plane = 3LL * Np;
+    const int k0 = kt * KT;
+
+    const double *xk[KT];
+    bool k_ok[KT];
+    double xb[KT][3], gt[KT][3];
+#pragma unroll
+    for (int t = 0; t < KT; t++) {
+        int k = k0 + t;
+        k_ok[t] = k < dm.S;
+        if (k >= dm.S) k = dm.S - 1;
+        xk[t] = ga.xs + ((long long)r * dm.S + k) * plane;
+        xb[t][0] = xk[t][bb]; xb[t][1] = xk[t][Np + bb]; xb[t][2] = xk[t][2 * Np + bb];
+        gt[t][0] = gt[t][1] = gt[t][2] = 0.0;
+    }
+    const double lam = ga.lammda ? ga.lammda[r] : 1.0;
+    const double bet = ga.beta ? ga.beta[r] : 1.0;
+    double e_nb = 0.0, e_bb = 0.0, e_sp = 0.0;
+    const bool want_grad = (ga.grad != nullptr) || (ga.p != nullptr);
+
+    // ---- 1. contact term ----------------------------------------------------------------
+    if ((ga.terms & 1) && want_grad && dm.M > 0) {
+        double acc[KT][3];
+#pragma unroll
+        for (int t = 0; t < KT; t++) acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
+        const long long off = dm.slice_off[sl];
+        const int width = dm.slice_w[sl];
+        const int *ej = dm.ent_j + off + lane;
+        const double *edc = dm.ent_dc + off + lane;
+        const double *ew = ga.wbuf + (long long)r * dm.tot + off + lane;
+        const double alpha = dm.alpha;
+        const double aa = __dmul_rn(alpha, alpha);
+        for (int e = 0; e < width; e++) {
+            const int o = ej[32 * e];
+            if (o < 0) continue;
+            const double dc = edc[32 * e];
+            const double w = ew[32 * e];
+#pragma unroll
+            for (int t = 0; t < KT; t++) {
+                const double ox = xk[t][o], oy = xk[t][Np + o], oz = xk[t][2 * Np + o];
+                if (EXACT) {
+                    // likelihoods_c.pyx:64-73 with d, sqrtdenoms recomputed as in pxd:33-37
+                    double d0 = __dsub_rn(xb[t][0], ox), d1 = __dsub_rn(xb[t][1], oy), d2 = __dsub_rn(xb[t][2], oz);
+                    double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+                    double d = __dsqrt_rn(s);
+                    double u = __dsub_rn(dc, d);
+                    double g = __dadd_rn(1.0, __dmul_rn(__dmul_rn(aa, u), u));
+                    double q = __dsqrt_rn(g);
+                    double f = __ddiv_rn(w, __dmul_rn(__dmul_rn(g, q), d));
+                    acc[t][0] = __dadd_rn(acc[t][0], __dmul_rn(__dsub_rn(ox, xb[t][0]), f));
+                    acc[t][1] = __dadd_rn(acc[t][1], __dmul_rn(__dsub_rn(oy, xb[t][1]), f));
+                    acc[t][2] = __dadd_rn(acc[t][2], __dmul_rn(__dsub_rn(oz, xb[t][2]), f));
+                } else {
+                    double dx = ox - xb[t][0], dy = oy - xb[t][1], dz = oz - xb[t][2];
+                    double s = fma(dz, dz, fma(dy, dy, dx * dx));
+                    double rd = rsqrt_nr(s);
+                    double tt = alpha * (dc - s * rd);
+                    double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                    double f = w * ((rq * rq) * (rq * rd));
+                    acc[t][0] = fma(f, dx, acc[t][0]);
+                    acc[t][1] = fma(f, dy, acc[t][1]);
+                    acc[t][2] = fma(f, dz, acc[t][2]);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < KT; t++) {
+            gt[t][0] = __dmul_rn(lam, acc[t][0]);
+            gt[t][1] = __dmul_rn(lam, acc[t][1]);
+            gt[t][2] = __dmul_rn(lam, acc[t][2]);
+        }
+    }
+
+    // ---- 2. nonbonded term (tiled all-pairs gather) ---------------------------------------
+    if (ga.terms & 2) {
+        double acc[KT][3], ea[KT];
+#pragma unroll
+        for (int t = 0; t < KT; t++) { acc[t][0] = acc[t][1] = acc[t][2] = 0.0; ea[t] = 0.0; }
+        const double rb = dm.radii[bb];
+        const double rb2 = __dmul_rn(rb, rb);
+        for (int o = 0; o < dm.N; o++) {
+            const double ro = dm.radii[o];
+            // forcefield_c.pyx:50: d < radii2[i] + radii2[j] + 2 * radii[i] * radii[j]
+            const double lim = EXACT
+                ? __dadd_rn(__dadd_rn(rb2, __dmul_rn(ro, ro)), __dmul_rn(__dmul_rn(2.0, rb), ro))
+                : (rb + ro) * (rb + ro);
+            const double d0sum = __dadd_rn(rb, ro);
+#pragma unroll
+            for (int t = 0; t < KT; t++) {
+                const double ox = xk[t][o], oy = xk[t][Np + o], oz = xk[t][2 * Np + o];
+                if (EXACT) {
+                    double d0 = __dsub_rn(xb[t][0], ox), d1 = __dsub_rn(xb[t][1], oy), d2 = __dsub_rn(xb[t][2], oz);
+                    double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+                    if (s < lim && o != b) {
+                        double d = __dsqrt_rn(s);
+                        double a = __dsub_rn(d0sum, d);
+                        double g = __ddiv_rn(__dmul_rn(__dmul_rn(a, a), a), d);
+                        acc[t][0] = __dadd_rn(acc[t][0], __dmul_rn(__dsub_rn(ox, xb[t][0]), g));
+                        acc[t][1] = __dadd_rn(acc[t][1], __dmul_rn(__dsub_rn(oy, xb[t][1]), g));
+                        acc[t][2] = __dadd_rn(acc[t][2], __dmul_rn(__dsub_rn(oz, xb[t][2]), g));
+                        double a2 = a * a;
+                        ea[t] += a2 * a2;
+                    }
+                } else {
+                    double dx = ox - xb[t][0], dy = oy - xb[t][1], dz = oz - xb[t][2];
+                    double s = fma(dz, dz, fma(dy, dy, dx * dx));
+                    if (s < lim && o != b) {
+                        double rd = rsqrt_nr(s);
+                        double a = d0sum - s * rd;
+                        double a2 = a * a;
+                        double g = a2 * a * rd;
+                        acc[t][0] = fma(g, dx, acc[t][0]);
+                        acc[t][1] = fma(g, dy, acc[t][1]);
+                        acc[t][2] = fma(g, dz, acc[t][2]);
+                        ea[t] += a2 * a2;
+                    }
+                }
+            }
+        }
+        // forcefield_c.pyx:59: force_constant * 2.0 * res ; nonbonded_prior.py:119-121: * beta
+        const double k2 = __dmul_rn(dm.k_nb, 2.0);
+#pragma unroll
+        for (int t = 0; t < KT; t++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                gt[t][c] = __dadd_rn(gt[t][c], __dmul_rn(bet, __dmul_rn(k2, acc[t][c])));
+            if (k_ok[t] && bead_ok) e_nb += ea[t];
+        }
+    }
+
+    // ---- 3a. backbone: bonds (b-1, b) then (b, b+1), the reference's visiting order --------
+    if (ga.terms & 4) {
+        const double kbb = dm.k_bb;
+        const bool has_prev = b > 0 && bead_ok && !isinf(dm.bb_ul[b - 1]);
+        const bool has_next = bead_ok && !isinf(dm.bb_ul[bb]);
+        const double ulp = has_prev ? dm.bb_ul[b - 1] : 0.0, llp = has_prev ? dm.bb_ll[b - 1] : 0.0;
+        const double uln = has_next ? dm.bb_ul[bb] : 0.0, lln = has_next ? dm.bb_ll[bb] : 0.0;
+#pragma unroll
+        for (int t = 0; t < KT; t++) {
+            double res[3] = {0.0, 0.0, 0.0};
+            if (has_prev) {   // i = b, i-1 = b-1 (backbone_prior_c.pyx:26-42)
+                double d0 = __dsub_rn(xb[t][0], xk[t][b - 1]);
+                double d1 = __dsub_rn(xb[t][1], xk[t][Np + b - 1]);
+                double d2 = __dsub_rn(xb[t][2], xk[t][2 * Np + b - 1]);
+                double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+                if (s > __dmul_rn(ulp, ulp)) {
+                    double d = __dsqrt_rn(s), a = __dsub_rn(d, ulp);
+                    res[0] = __ddiv_rn(__dmul_rn(a, d0), d);
+                    res[1] = __ddiv_rn(__dmul_rn(a, d1), d);
+                    res[2] = __ddiv_rn(__dmul_rn(a, d2), d);
+                    if (k_ok[t]) e_bb += a * a;
+                } else if (s < __dmul_rn(llp, llp)) {
+                    double d = __dsqrt_rn(s), a = __dsub_rn(llp, d);
+                    res[0] = -__ddiv_rn(__dmul_rn(a, d0), d);
+                    res[1] = -__ddiv_rn(__dmul_rn(a, d1), d);
+                    res[2] = -__ddiv_rn(__dmul_rn(a, d2), d);
+                    if (k_ok[t]) e_bb += a * a;
+                }
+            }
+            if (has_next) {   // i = b+1, i-1 = b
+                double d0 = __dsub_rn(xk[t][b + 1], xb[t][0]);
+                double d1 = __dsub_rn(xk[t][Np + b + 1], xb[t][1]);
+                double d2 = __dsub_rn(xk[t][2 * Np + b + 1], xb[t][2]);
+                double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+                if (s > __dmul_rn(uln, uln)) {
+                    double d = __dsqrt_rn(s), a = __dsub_rn(d, uln);
+                    res[0] = __dsub_rn(res[0], __ddiv_rn(__dmul_rn(a, d0), d));
+                    res[1] = __dsub_rn(res[1], __ddiv_rn(__dmul_rn(a, d1), d));
+                    res[2] = __dsub_rn(res[2], __ddiv_rn(__dmul_rn(a, d2), d));
+                } else if (s < __dmul_rn(lln, lln)) {
+                    double d = __dsqrt_rn(s), a = __dsub_rn(lln, d);
+                    res[0] = __dadd_rn(res[0], __ddiv_rn(__dmul_rn(a, d0), d));
+                    res[1] = __dadd_rn(res[1], __ddiv_rn(__dmul_rn(a, d1), d));
+                    res[2] = __dadd_rn(res[2], __ddiv_rn(__dmul_rn(a, d2), d));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) gt[t][c] = __dadd_rn(gt[t][c], __dmul_rn(kbb, res[c]));
+        }
+    }
+
+    // ---- 3b. sphere (sphere_prior_c.pyx:25-36) ---------------------------------------------
+    if ((ga.terms & 8) && dm.sphere_active) {
+        const double rb = dm.radii[bb];
+        const double R0 = dm.sph_R;
+        // radius2 + bead_radii2[i] - 2 * radius * bead_radii[i]
+        const double lim = __dsub_rn(__dadd_rn(__dmul_rn(R0, R0), __dmul_rn(rb, rb)),
+                                     __dmul_rn(__dmul_rn(2.0, R0), rb));
+#pragma unroll
+        for (int t = 0; t < KT; t++) {
+            double d0 = __dsub_rn(xb[t][0], dm.sph_cx), d1 = __dsub_rn(xb[t][1], dm.sph_cy),
+                   d2 = __dsub_rn(xb[t][2], dm.sph_cz);
+            double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+            if (!(s < lim)) {
+                double d = __dsqrt_rn(s);
+                double a = __dsub_rn(__dadd_rn(d, rb), R0);
+                double f = __ddiv_rn(a, d);
+                gt[t][0] = __dadd_rn(gt[t][0], __dmul_rn(dm.sph_k, __dmul_rn(d0, f)));
+                gt[t][1] = __dadd_rn(gt[t][1], __dmul_rn(dm.sph_k, __dmul_rn(d1, f)));
+                gt[t][2] = __dadd_rn(gt[t][2], __dmul_rn(dm.sph_k, __dmul_rn(d2, f)));
+                // sphere_prior.py:70-72 penalises d + r > R only
+                if (k_ok[t] && bead_ok && a > 0.0) e_sp += a * a;
+            }
+        }
+    }
+
+    // ---- 4. epilogue ----------------------------------------------------------------------
+    double kin = 0.0;
+#pragma unroll
+    for (int t = 0; t < KT; t++) {
+        if (!(k_ok[t] && bead_ok)) continue;
+        const int k = k0 + t;
+        const long long at = (((long long)r * dm.S + k) * dm.N + b) * 3;
+        if (ga.grad) {
+            ga.grad[at] = gt[t][0]; ga.grad[at + 1] = gt[t][1]; ga.grad[at + 2] = gt[t][2];
+        }
+        if (ga.p) {
+            const double eps = ga.eps[r];
+            double p0 = ga.p[at], p1 = ga.p[at + 1], p2 = ga.p[at + 2];
+            if (ga.kinetic_before == 1) kin += p0 * p0 + p1 * p1 + p2 * p2;
+            const double ke = ga.kick * eps;
+            p0 = fma(-ke, gt[t][0], p0); p1 = fma(-ke, gt[t][1], p1); p2 = fma(-ke, gt[t][2], p2);
+            ga.p[at] = p0; ga.p[at + 1] = p1; ga.p[at + 2] = p2;
+            if (ga.kinetic_before == 2) kin += p0 * p0 + p1 * p1 + p2 * p2;
+            if (ga.xs_next) {
+                double *xn = ga.xs_next + ((long long)r * dm.S + k) * plane;
+                xn[b] = fma(eps, p0, xb[t][0]);
+                xn[Np + b] = fma(eps, p1, xb[t][1]);
+                xn[2 * Np + b] = fma(eps, p2, xb[t][2]);
+            }
+        }
+    }
+    if (ga.partB) {
+        e_nb = warp_sum(e_nb); e_bb = warp_sum(e_bb); e_sp = warp_sum(e_sp); kin = warp_sum(kin);
+        if (lane == 0) {
+            double *o = ga.partB + item * 4;
+            o[0] = e_nb; o[1] = e_bb; o[2] = e_sp; o[3] = kin;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fixed-order reduction of the per-block / per-warp partials into E[R][4] (+ H[R][.]).
+__global__ void __launch_bounds__(256)
+finalize_kernel(DevModel dm, const double *__restrict__ partA, int nA,
+                const double *__restrict__ partB, long long itemsB_per_replica,
+                double *__restrict__ energies, double *__restrict__ kinetic)
+{
+    const int r = blockIdx.x;
+    __shared__ double sh[5][256];
+    double a = 0.0, e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+    if (partA)
+        for (int q = threadIdx.x; q < nA; q += 256) a += partA[(long long)r * nA + q];
+    if (partB)
+        for (long long q = threadIdx.x; q < itemsB_per_replica; q += 256) {
+            const double *o = partB + ((long long)r * itemsB_per_replica + q) * 4;
+            e0 += o[0]; e1 += o[1]; e2 += o[2]; e3 += o[3];
+        }
+    sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = e0; sh[2][threadIdx.x] = e1;
+    sh[3][threadIdx.x] = e2; sh[4][threadIdx.x] = e3;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+#pragma unroll
+            for (int q = 0; q < 5; q++) sh[q][threadIdx.x] += sh[q][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (energies) {
+            double *E = energies + (long long)r * 4;
+            E[0] = -sh[0][0];                         // -log L
+            E[1] = 0.25 * dm.k_nb * sh[1][0];         // each pair visited from both ends: k/2 * 1/2
+            E[2] = 0.5 * dm.k_bb * sh[2][0];
+            E[3] = 0.5 * dm.sph_k * sh[3][0];
+        }
+        if (kinetic) kinetic[r] = 0.5 * sh[4][0];
+    }
+}
+
+// H[r][slot] = lammda*E0 + beta*E1 + E2 + E3 ; H[r][slot+1] = K
+__global__ void hamiltonian_kernel(const double *__restrict__ energies, const double *__restrict__ kinetic,
+                                   const double *__restrict__ lammda, const double *__restrict__ beta,
+                                   double *__restrict__ H, int slot, int R)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const double *E = energies + (long long)r * 4;
+    double lam = lammda ? lammda[r] : 1.0, bet = beta ? beta[r] : 1.0;
+    H[(long long)r * 4 + slot] = lam * E[0] + bet * E[1] + E[2] + E[3];
+    H[(long long)r * 4 + slot + 1] = kinetic[r];
+}
+
+__global__ void select_kernel(int R, long long n, const int *__restrict__ mask,
+                              const double *__restrict__ src, double *__restrict__ dst)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)R * n) return;
+    int r = (int)(t / n);
+    if (mask[r]) dst[t] = src[t];
+}
+
+// ---------------------------------------------------------------------------------------
+// Neighbour list of one structure (c/nblist.c:181-303): membership |dx|^2 <= cutoff^2 with
+// the dot product associated as mathutils.c:13-15 and no FMA contraction.
+__global__ void nblist_count_kernel(const double *__restrict__ x, int N, double cut2, int *__restrict__ counts)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+    int c = 0;
+    for (int j = i + 1; j < N; j++) {
+        double d0 = __dsub_rn(xi, x[3 * j]), d1 = __dsub_rn(yi, x[3 * j + 1]), d2 = __dsub_rn(zi, x[3 * j + 2]);
+        double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+        if (!(s > cut2)) c++;
+    }
+    counts[i] = c;
+}
+
+__global__ void nblist_fill_kernel(const double *__restrict__ x, int N, double cut2,
+                                   const long long *__restrict__ offsets, int *__restrict__ pairs, long long capacity)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+    long long w = offsets[i];
+    for (int j = i + 1; j < N; j++) {
+        double d0 = __dsub_rn(xi, x[3 * j]), d1 = __dsub_rn(yi, x[3 * j + 1]), d2 = __dsub_rn(zi, x[3 * j + 2]);
+        double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+        if (!(s > cut2)) {
+            if (w < capacity) { pairs[2 * w] = i; pairs[2 * w + 1] = j; }
+            w++;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// FMA issue-rate micro-benchmarks (roofline denominators for the FP64 / FP32 pipes).
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T *out, int iters, T a, T b)
+{
+    T v0 = (T)threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            v0 = v0 * a + b; v1 = v1 * a + b; v2 = v2 * a + b; v3 = v3 * a + b;
+            v4 = v4 * a + b; v5 = v5 * a + b; v6 = v6 * a + b; v7 = v7 * a + b;
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
+
+}  // namespace ehic

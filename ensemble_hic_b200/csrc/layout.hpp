@@ -1,0 +1,121 @@
+// layout.hpp -- host-side construction of the contact-list layout walked by the kernels.
+//
+// The reference walks data_points[M][3] row by row for every structure
+// (evaluate_FWM_pureC.pxd:29-39, likelihoods_c.pyx:62-73) and scatter-adds into both beads
+// of each pair.  The GPU path instead uses two static views of the same list, built once
+// per model:
+//
+//  (1) the PAIR view: rows sorted by (i, j) so that one warp of the forward kernel reads a
+//      run of pairs sharing bead i with consecutive beads j (coalesced coordinate loads);
+//      `perm` maps a sorted position back to the row of data_points.
+//  (2) the ROW view (sliced ELL, slice height 32 = one warp): for every bead b the list of
+//      its partners o, so that the gradient is a gather  g_b += f_m * (x_o - x_b)  with no
+//      atomics and a fixed summation order.  Slice s holds beads 32s..32s+31; entry e of
+//      lane l lives at slice_off[s] + 32*e + l (coalesced across the warp).  Row order is
+//      ascending partner index (fast mode) or data-point order (exact mode, which makes the
+//      per-bead summation order identical to likelihoods_c.pyx:62-73).
+//      slot_a[m] / slot_b[m] are the ROW-view positions of sorted pair m in row i and row j:
+//      the forward kernel scatters the per-pair weight there.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace ehic {
+
+struct ContactLayout {
+    int32_t N = 0;
+    int64_t M = 0;
+    // pair view (length M, sorted by (i, j))
+    std::vector<int32_t> pi, pj;
+    std::vector<double> pdc, pcnt;
+    std::vector<int64_t> perm;
+    std::vector<int32_t> slot_a, slot_b;
+    // row view
+    int32_t n_slices = 0;
+    std::vector<int64_t> slice_off;   // n_slices + 1, in entries
+    std::vector<int32_t> slice_w;     // n_slices
+    std::vector<int32_t> row_len;     // N
+    std::vector<int32_t> ent_j;       // tot, -1 = padding
+    std::vector<double> ent_dc;       // tot
+    int64_t tot = 0;
+};
+
+// Returns "" on success, otherwise an error message.
+inline std::string build_layout(int32_t N, int64_t M, const int64_t *data, const double *cds,
+                                bool exact_order, ContactLayout &L, bool want_values = true)
+{
+    L = ContactLayout();
+    L.N = N; L.M = M;
+    if (N <= 0) return "n_beads must be positive";
+    if (M < 0) return "n_data must be non-negative";
+    for (int64_t m = 0; m < M; m++) {
+        int64_t i = data[3 * m], j = data[3 * m + 1];
+        if (i < 0 || i >= N || j < 0 || j >= N)
+            return "data point " + std::to_string(m) + " has a bead index outside [0, n_beads)";
+        if (i == j)
+            return "data point " + std::to_string(m) + " pairs a bead with itself (distance 0)";
+    }
+    // (1) pair view: stable sort of the rows by (i, j)
+    L.perm.resize(M);
+    std::iota(L.perm.begin(), L.perm.end(), (int64_t)0);
+    std::stable_sort(L.perm.begin(), L.perm.end(), [&](int64_t a, int64_t b) {
+        int64_t ka = data[3 * a] * (int64_t)N + data[3 * a + 1];
+        int64_t kb = data[3 * b] * (int64_t)N + data[3 * b + 1];
+        return ka < kb;
+    });
+    L.pi.resize(M); L.pj.resize(M);
+    if (want_values) { L.pdc.resize(M); L.pcnt.resize(M); }
+    for (int64_t s = 0; s < M; s++) {
+        int64_t m = L.perm[s];
+        L.pi[s] = (int32_t)data[3 * m];
+        L.pj[s] = (int32_t)data[3 * m + 1];
+        if (want_values) { L.pdc[s] = cds[m]; L.pcnt[s] = (double)data[3 * m + 2]; }
+    }
+    // (2) row view
+    L.row_len.assign(N, 0);
+    for (int64_t s = 0; s < M; s++) { L.row_len[L.pi[s]]++; L.row_len[L.pj[s]]++; }
+    L.n_slices = (N + 31) / 32;
+    L.slice_off.assign(L.n_slices + 1, 0);
+    L.slice_w.assign(L.n_slices, 0);
+    for (int32_t sl = 0; sl < L.n_slices; sl++) {
+        int32_t w = 0;
+        for (int32_t b = sl * 32; b < std::min(N, sl * 32 + 32); b++) w = std::max(w, L.row_len[b]);
+        L.slice_w[sl] = w;
+        L.slice_off[sl + 1] = L.slice_off[sl] + (int64_t)32 * w;
+    }
+    L.tot = L.slice_off[L.n_slices];
+    if (L.tot >= ((int64_t)1 << 31)) return "contact list too large for 32-bit row slots";
+    L.ent_j.assign(L.tot, -1);
+    if (want_values) L.ent_dc.assign(L.tot, 0.0);
+    L.slot_a.resize(M); L.slot_b.resize(M);
+    std::vector<int32_t> fill(N, 0);
+    auto place = [&](int32_t b, int32_t o, int64_t s, bool first) {
+        int64_t pos = L.slice_off[b / 32] + (int64_t)32 * fill[b] + (b % 32);
+        fill[b]++;
+        L.ent_j[pos] = o;
+        if (want_values) L.ent_dc[pos] = L.pdc[s];
+        (first ? L.slot_a : L.slot_b)[s] = (int32_t)pos;
+    };
+    if (exact_order) {
+        // rows in data-point order: walk the ORIGINAL list; inv maps original row -> sorted position
+        std::vector<int64_t> inv(M);
+        for (int64_t s = 0; s < M; s++) inv[L.perm[s]] = s;
+        for (int64_t m = 0; m < M; m++) {
+            int64_t s = inv[m];
+            place(L.pi[s], L.pj[s], s, true);
+            place(L.pj[s], L.pi[s], s, false);
+        }
+    } else {
+        // walking the (i, j)-sorted list yields, for i < j lists, partners in ascending order
+        for (int64_t s = 0; s < M; s++) {
+            place(L.pi[s], L.pj[s], s, true);
+            place(L.pj[s], L.pi[s], s, false);
+        }
+    }
+    return "";
+}
+
+}  // namespace ehic

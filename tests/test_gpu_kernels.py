@@ -1,0 +1,203 @@
+"""GPU parity of the CUDA kernels (through the C ABI) against the CPU oracle.
+
+FP64 tolerances: north_star asks for 1e-10 relative on log-posterior and gradient; the
+tests below hold the fast mode to 1e-12 (max-norm relative) and the exact mode to
+bit-for-bit equality with the reference's Cython arithmetic (oracle == oracle/_ref bit for
+bit, see tests/test_oracle.py)."""
+import numpy as np
+import pytest
+
+from helpers import make_problem, relerr
+
+pytestmark = pytest.mark.gpu
+
+FAST_TOL = 1e-12
+
+
+def _model(pb, exact, **kw):
+    from ensemble_hic_b200.engine import Model
+    kw.setdefault("k_nb", 50.0)
+    kw.setdefault("k_bb", 500.0)
+    return Model(pb["S"], pb["radii"], pb["data"], pb["cds"], alpha=pb["alpha"], exact=exact, **kw)
+
+
+@pytest.mark.parametrize("S,N", [(1, 5), (2, 23), (3, 40), (5, 70), (7, 33)])
+def test_mock_data_exact_is_bitexact(co, S, N):
+    pb = make_problem(seed=S * 100 + N, S=S, N=N)
+    m = _model(pb, True)
+    md = m.mock_data(pb["X"], pb["norm"])[0]
+    ref = co.ensemble_contacts_evaluate(pb["X"], pb["norm"], pb["cds"], pb["alpha"], pb["data"])
+    assert np.array_equal(md, ref)
+
+
+@pytest.mark.parametrize("S,N", [(1, 5), (2, 23), (3, 40), (5, 70), (8, 64)])
+def test_mock_data_fast(co, S, N):
+    pb = make_problem(seed=S * 100 + N, S=S, N=N)
+    m = _model(pb, False)
+    md = m.mock_data(pb["X"], pb["norm"])[0]
+    ref = co.ensemble_contacts_evaluate(pb["X"], pb["norm"], pb["cds"], pb["alpha"], pb["data"])
+    assert relerr(md, ref) < FAST_TOL
+    np.testing.assert_allclose(md, ref, rtol=1e-10, atol=1e-14 * pb["norm"] * S)
+
+
+@pytest.mark.parametrize("S,N,density", [(1, 5, 1.0), (2, 23, 1.0), (3, 40, 0.3), (5, 70, 1.0), (6, 100, 0.2)])
+def test_likelihood_gradient_exact_is_bitexact(co, S, N, density):
+    from ensemble_hic_b200.engine import TERM_LIKELIHOOD
+    pb = make_problem(seed=7 + S * 100 + N, S=S, N=N, density=density)
+    m = _model(pb, True)
+    g = m.evaluate(pb["X"], pb["norm"], terms=TERM_LIKELIHOOD)["grad"][0]
+    ref = co.calculate_gradient(pb["X"], pb["alpha"], pb["norm"], pb["cds"], pb["data"])
+    assert np.array_equal(g, ref)
+
+
+@pytest.mark.parametrize("S,N,density", [(1, 5, 1.0), (2, 23, 1.0), (3, 40, 0.3), (5, 70, 1.0), (9, 100, 0.2)])
+def test_likelihood_gradient_fast(co, S, N, density):
+    from ensemble_hic_b200.engine import TERM_LIKELIHOOD
+    pb = make_problem(seed=7 + S * 100 + N, S=S, N=N, density=density)
+    m = _model(pb, False)
+    g = m.evaluate(pb["X"], pb["norm"], terms=TERM_LIKELIHOOD)["grad"][0]
+    ref = co.calculate_gradient(pb["X"], pb["alpha"], pb["norm"], pb["cds"], pb["data"])
+    assert relerr(g, ref) < FAST_TOL
+
+
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("uniform", [True, False])
+def test_nonbonded_gradient_and_energy(co, exact, uniform):
+    from ensemble_hic_b200.engine import TERM_NONBONDED
+    pb = make_problem(seed=11, S=4, N=90, uniform_radii=uniform, step=0.6)
+    m = _model(pb, exact, k_nb=50.0)
+    out = m.evaluate(pb["X"], pb["norm"], terms=TERM_NONBONDED, energies=True)
+    r = pb["radii"]
+    ref_g = np.concatenate([co.forcefield_gradient(x, r, r * r, 50.0) for x in pb["X"]])
+    ref_E = sum(co.forcefield_energy(x, r, r * r, 50.0) for x in pb["X"])
+    assert np.abs(ref_g).max() > 0
+    if exact:
+        assert np.array_equal(out["grad"][0], ref_g)
+    else:
+        assert relerr(out["grad"][0], ref_g) < FAST_TOL
+    assert abs(out["energies"][0, 1] - ref_E) <= 1e-12 * abs(ref_E)
+
+
+def test_nonbonded_matches_neighbour_list_path(co):
+    """production reference path: NBList + PROLSQ (c/nblist.c, c/forcefield.c, c/prolsq.c)."""
+    from oracle.oracle import OracleNBLForceField
+    from ensemble_hic_b200.engine import TERM_NONBONDED
+    pb = make_problem(seed=12, S=3, N=120, step=0.6)
+    ff = OracleNBLForceField(co, pb["radii"], 50.0)
+    m = _model(pb, False, k_nb=50.0)
+    out = m.evaluate(pb["X"], pb["norm"], terms=TERM_NONBONDED, energies=True)
+    ref_g = np.concatenate([ff.gradient(x) for x in pb["X"]])
+    ref_E = sum(ff.energy(x) for x in pb["X"])
+    assert relerr(out["grad"][0], ref_g) < FAST_TOL
+    assert abs(out["energies"][0, 1] - ref_E) <= 1e-12 * abs(ref_E)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_backbone_gradient_bitexact_and_energy(co, exact):
+    from oracle.oracle import backbone_log_prob_single
+    from ensemble_hic_b200.engine import TERM_BACKBONE
+    pb = make_problem(seed=13, S=3, N=50, step=1.0)
+    N = pb["N"]
+    rng = np.random.default_rng(5)
+    ll = rng.uniform(0.6, 0.9, N - 1); ul = rng.uniform(0.95, 1.2, N - 1)
+    mr = np.array([0, 20, 21, 50])      # includes a single-bead molecule
+    m = _model(pb, exact, k_bb=7.5, bb_lower=ll, bb_upper=ul, mol_ranges=mr)
+    out = m.evaluate(pb["X"], pb["norm"], terms=TERM_BACKBONE, energies=True)
+    ref = []; E = 0.0
+    for x in pb["X"]:
+        for a, b in zip(mr[:-1], mr[1:]):
+            ref.append(co.backbone_prior_gradient(x[a:b].ravel(), ll[a:b - 1], ul[a:b - 1], 7.5))
+            E -= backbone_log_prob_single(x[a:b], ll[a:b - 1], ul[a:b - 1], 7.5)
+    ref = np.concatenate(ref)
+    assert np.abs(ref).max() > 0
+    assert np.array_equal(out["grad"][0], ref)      # the backbone term uses IEEE ops in both modes
+    assert abs(out["energies"][0, 2] - E) <= 1e-12 * abs(E)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_sphere_gradient_bitexact_and_energy(co, exact):
+    from oracle.oracle import sphere_log_prob_single
+    from ensemble_hic_b200.engine import TERM_SPHERE
+    pb = make_problem(seed=14, S=3, N=60, uniform_radii=False, step=1.5)
+    c = np.array([0.3, -0.2, 0.1])
+    m = _model(pb, exact, sphere=(3.0, 5.0, c))
+    out = m.evaluate(pb["X"], pb["norm"], terms=TERM_SPHERE, energies=True)
+    r = pb["radii"]
+    ref = np.concatenate([co.sphere_prior_gradient(x, c, 3.0, 5.0, np.arange(len(x)), r, r * r) for x in pb["X"]])
+    E = -sum(sphere_log_prob_single(x, c, 3.0, 5.0, r) for x in pb["X"])
+    assert np.abs(ref).max() > 0
+    assert np.array_equal(out["grad"][0], ref)
+    assert abs(out["energies"][0, 3] - E) <= 1e-12 * abs(E)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_full_posterior_batched_replicas(co, exact):
+    """R replicas with different (x, norm, lammda, beta) in one call == R oracle evaluations."""
+    from oracle.oracle import OraclePosterior
+    pb = make_problem(seed=21, S=4, N=48, step=0.8)
+    N, S = pb["N"], pb["S"]
+    ul = pb["radii"][:-1] + pb["radii"][1:]
+    sphere = (4.0, 5.0, np.zeros(3))
+    op = OraclePosterior(S, pb["data"], pb["cds"], pb["alpha"], pb["radii"], 50.0, 500.0,
+                         [np.zeros(N - 1)], [ul], [0, N], sphere=sphere, nonbonded="nbl")
+    R = 5
+    rng = np.random.default_rng(3)
+    X = np.stack([pb["X"] + rng.normal(scale=0.05, size=pb["X"].shape) for _ in range(R)])
+    norm = rng.uniform(1, 5, R); lam = np.linspace(0.0, 1.0, R); bet = np.linspace(0.001, 1.0, R)
+    m = _model(pb, exact, sphere=sphere, max_replicas=R)
+    out = m.evaluate(X, norm, lam, bet, energies=True, md=True)
+    for r in range(R):
+        g = op.gradient(X[r], norm[r], lam[r], bet[r])
+        assert relerr(out["grad"][r], g) < FAST_TOL
+        E = op.energies(X[r], norm[r])
+        for q in range(4):
+            assert abs(out["energies"][r, q] - E[q]) <= 1e-11 * max(abs(E[q]), 1e-300), (r, q)
+        lp = -lam[r] * out["energies"][r, 0] - bet[r] * out["energies"][r, 1] - out["energies"][r, 2] - out["energies"][r, 3]
+        assert abs(lp - op.log_prob(X[r], norm[r], lam[r], bet[r])) <= 1e-10 * abs(lp)
+        assert relerr(out["md"][r], op.mock_data(X[r], norm[r])) < FAST_TOL
+
+
+def test_neighbour_list_is_bitexact(co):
+    from oracle.oracle import OracleNBList
+    from ensemble_hic_b200.engine import nblist_pairs
+    pb = make_problem(seed=31, S=1, N=300, step=0.5)
+    x = pb["X"][0]
+    cutoff = 1.0 + 1e-3
+    nb = OracleNBList(co, cutoff, 90, 300, 300)
+    n = nb.update(x, 1)
+    pairs = nblist_pairs(x, cutoff)
+    assert n == len(pairs) and n > 300
+    assert np.array_equal(pairs, nb.canonical_pairs())
+
+
+def test_hmc_trajectory_matches_oracle_leapfrog(co):
+    import torch
+    from oracle.oracle import OraclePosterior, leapfrog
+    pb = make_problem(seed=41, S=2, N=23, radius=1.0, cd_factor=2.0, min_sep=2, step=1.8)
+    N, S = pb["N"], pb["S"]
+    ul = pb["radii"][:-1] + pb["radii"][1:]
+    sphere = (10.0, 5.0, np.zeros(3))
+    op = OraclePosterior(S, pb["data"], pb["cds"], pb["alpha"], pb["radii"], 50.0, 1000.0,
+                         [np.zeros(N - 1)], [ul], [0, N], sphere=sphere, nonbonded="nbl")
+    R, L = 2, 20
+    rng = np.random.default_rng(0)
+    X = np.stack([pb["X"], pb["X"] + rng.normal(scale=0.1, size=pb["X"].shape)]).reshape(R, -1)
+    P = rng.normal(size=X.shape)
+    norm = np.array([2.5, 3.5]); lam = np.array([0.3, 1.0]); bet = np.array([0.5, 1.0]); eps = np.array([1e-3, 2e-3])
+    m = _model(pb, False, k_nb=50.0, k_bb=1000.0, sphere=sphere, max_replicas=R)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
+    m.hmc_trajectory_device(R, L, x_t, p_t, t(norm), t(lam), t(bet), t(eps), H_t)
+    torch.cuda.synchronize()
+    H = H_t.cpu().numpy()
+    for r in range(R):
+        grad = lambda x: op.gradient(x, norm[r], lam[r], bet[r])
+        x1, p1 = leapfrog(grad, X[r], P[r], eps[r], L)
+        assert relerr(x_t[r].cpu().numpy(), x1) < 1e-11
+        assert relerr(p_t[r].cpu().numpy(), p1) < 1e-9
+        E0 = -op.log_prob(X[r], norm[r], lam[r], bet[r]); E1 = -op.log_prob(x1, norm[r], lam[r], bet[r])
+        assert abs(H[r, 0] - E0) <= 1e-10 * abs(E0)
+        assert abs(H[r, 2] - E1) <= 1e-10 * abs(E1)
+        assert abs(H[r, 1] - 0.5 * np.sum(P[r] ** 2)) <= 1e-12 * H[r, 1]
+        assert abs(H[r, 3] - 0.5 * np.sum(p1 ** 2)) <= 1e-9 * H[r, 3]
