@@ -42,10 +42,13 @@ struct ehic_model {
     std::vector<void *> owned;      // device allocations
     // workspace
     double *xs[2] = {nullptr, nullptr};
-    double *wbuf = nullptr, *partA = nullptr, *partB = nullptr;
+    double *wbuf = nullptr, *gprior = nullptr;
+    double *partA = nullptr, *partP = nullptr, *partK = nullptr;
     double *energies = nullptr, *kinetic = nullptr;
     int nA = 0;                     // forward blocks per replica
-    int kt = 1, nkt = 1;
+    int nPx = 0;                    // prior blocks per structure
+    int kt = 1, nkt = 1, nktg = 1;  // structures per warp, tiles per replica, tile groups (4 warps) per slice
+    double r_max = 0.0;
     // staging for the host entry points
     double *st_x = nullptr, *st_g = nullptr, *st_md = nullptr, *st_small = nullptr;
     cudaStream_t st_stream = nullptr;
@@ -161,7 +164,9 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
 
     DevModel &dm = m->dm;
     dm.N = N; dm.S = S; dm.Np = (N + 31) / 32 * 32; dm.n_slices = L.n_slices;
-    dm.M = L.M; dm.tot = L.tot;
+    dm.M = L.M; dm.tot = L.tot; dm.wstride = L.tot + ContactLayout::kTailPad;
+    static_assert(ContactLayout::kTailPad == EHIC_CHUNK * 32, "tail pad must cover one pipeline chunk");
+    for (int b = 0; b < N; b++) m->r_max = std::max(m->r_max, desc->bead_radii[b]);
     dm.alpha = desc->alpha; dm.k_nb = desc->nonbonded_k; dm.k_bb = desc->backbone_k;
     dm.sphere_active = desc->sphere_active;
     dm.sph_R = desc->sphere_radius; dm.sph_k = desc->sphere_k;
@@ -182,19 +187,23 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
 
     m->kt = pick_kt(S);
     m->nkt = (S + m->kt - 1) / m->kt;
+    m->nktg = (m->nkt + EHIC_GATHER_WARPS - 1) / EHIC_GATHER_WARPS;
     m->nA = (int)((L.M + 255) / 256);
+    m->nPx = (N + EHIC_PRIOR_THREADS - 1) / EHIC_PRIOR_THREADS;
     const size_t Rm = (size_t)desc->max_replicas;
     const size_t xs_n = Rm * S * 3 * (size_t)dm.Np;
 #define DA(ptr, n)                                                   \
     do { rc = dalloc(m, &(ptr), (n)); if (rc) { ehic_model_destroy(m); return rc; } } while (0)
     DA(m->xs[0], xs_n); DA(m->xs[1], xs_n);
-    DA(m->wbuf, Rm * (size_t)L.tot);
+    DA(m->wbuf, Rm * (size_t)dm.wstride);
+    DA(m->gprior, Rm * S * (size_t)N * 3);
     DA(m->partA, Rm * (size_t)std::max(m->nA, 1));
-    DA(m->partB, Rm * (size_t)L.n_slices * m->nkt * 4);
+    DA(m->partP, Rm * (size_t)S * m->nPx * 3);
+    DA(m->partK, Rm * (size_t)L.n_slices * m->nktg * EHIC_GATHER_WARPS);
     DA(m->energies, Rm * 4); DA(m->kinetic, Rm);
 #undef DA
     // weights of padding slots are never read (ent_j < 0), but keep the buffer defined
-    if (cudaMemset(m->wbuf, 0, std::max<size_t>(Rm * (size_t)L.tot, 1) * sizeof(double)) != cudaSuccess) {
+    if (cudaMemset(m->wbuf, 0, Rm * (size_t)dm.wstride * sizeof(double)) != cudaSuccess) {
         ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed");
     }
     if (cudaStreamCreateWithFlags(&m->st_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -295,15 +304,29 @@ static int launch_forward(ehic_model *m, int R, const double *xs, const double *
     return EHIC_OK;
 }
 
+static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const double *d_beta,
+                        bool want_grad, bool want_energy, cudaStream_t st)
+{
+    dim3 grid((unsigned)m->nPx, (unsigned)m->dm.S, (unsigned)R);
+    double *gp = want_grad ? m->gprior : nullptr, *pp = want_energy ? m->partP : nullptr;
+    if (m->flags & EHIC_FLAG_EXACT)
+        prior_kernel<true><<<grid, EHIC_PRIOR_THREADS, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max);
+    else
+        prior_kernel<false><<<grid, EHIC_PRIOR_THREADS, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return EHIC_OK;
+}
+
 template <bool EXACT>
 static void launch_gather_t(ehic_model *m, const GatherArgs &ga, int R, cudaStream_t st)
 {
-    long long items = (long long)R * m->dm.n_slices * m->nkt;
-    unsigned blocks = (unsigned)((items + 3) / 4);
+    unsigned blocks = (unsigned)((long long)R * m->dm.n_slices * m->nktg);
+    const int threads = EHIC_GATHER_WARPS * 32;
     switch (m->kt) {
-    case 4: gather_kernel<EXACT, 4><<<blocks, 128, 0, st>>>(m->dm, ga, R, m->nkt); break;
-    case 2: gather_kernel<EXACT, 2><<<blocks, 128, 0, st>>>(m->dm, ga, R, m->nkt); break;
-    default: gather_kernel<EXACT, 1><<<blocks, 128, 0, st>>>(m->dm, ga, R, m->nkt); break;
+    case 4: gather_kernel<EXACT, 4><<<blocks, threads, 0, st>>>(m->dm, ga, m->nkt, m->nktg); break;
+    case 2: gather_kernel<EXACT, 2><<<blocks, threads, 0, st>>>(m->dm, ga, m->nkt, m->nktg); break;
+    default: gather_kernel<EXACT, 1><<<blocks, threads, 0, st>>>(m->dm, ga, m->nkt, m->nktg); break;
     }
     LAUNCHED();
 }
@@ -316,10 +339,13 @@ static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_
     return EHIC_OK;
 }
 
-static int launch_finalize(ehic_model *m, int R, bool haveA, bool haveB, double *d_energies, double *d_kin, cudaStream_t st)
+static int launch_finalize(ehic_model *m, int R, bool haveA, bool haveP, bool haveK,
+                           double *d_energies, double *d_kin, cudaStream_t st)
 {
-    finalize_kernel<<<R, 256, 0, st>>>(m->dm, haveA ? m->partA : nullptr, m->nA, haveB ? m->partB : nullptr,
-                                       (long long)m->dm.n_slices * m->nkt, d_energies, d_kin);
+    finalize_kernel<<<R, 256, 0, st>>>(m->dm, haveA ? m->partA : nullptr, m->nA,
+                                       haveP ? m->partP : nullptr, (long long)m->dm.S * m->nPx,
+                                       haveK ? m->partK : nullptr, (long long)m->dm.n_slices * m->nktg * EHIC_GATHER_WARPS,
+                                       d_energies, d_kin);
     LAUNCHED();
     CU(cudaGetLastError());
     return EHIC_OK;
@@ -350,6 +376,7 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     terms &= EHIC_TERM_ALL;
     if (!m->dm.sphere_active) terms &= ~EHIC_TERM_SPHERE;
     const bool lik = (terms & EHIC_TERM_LIKELIHOOD) != 0;
+    const int prior_terms = terms & ~EHIC_TERM_LIKELIHOOD;
     if ((lik || d_md) && !d_norm) return fail(EHIC_ERR_INVALID, "norm required for the likelihood term");
     cudaStream_t st = (cudaStream_t)stream;
     rc = launch_pack(m, R, d_x, m->xs[0], st);
@@ -359,16 +386,21 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
         rc = launch_forward(m, R, m->xs[0], d_norm, d_md, lik && d_grad, lik && d_energies, st);
         if (rc) return rc;
     }
-    const bool need_gather = d_grad || (d_energies && (terms & ~EHIC_TERM_LIKELIHOOD));
-    if (need_gather) {
+    const bool need_prior = prior_terms && (d_grad || d_energies);
+    if (need_prior) {
+        rc = launch_prior(m, R, prior_terms, m->xs[0], d_beta, d_grad != nullptr, d_energies != nullptr, st);
+        if (rc) return rc;
+    }
+    if (d_grad) {
         GatherArgs ga{};
-        ga.xs = m->xs[0]; ga.wbuf = m->wbuf; ga.lammda = d_lammda; ga.beta = d_beta;
-        ga.grad = d_grad; ga.partB = d_energies ? m->partB : nullptr; ga.terms = terms;
+        ga.xs = m->xs[0]; ga.wbuf = m->wbuf; ga.lammda = d_lammda;
+        ga.gprior = need_prior ? m->gprior : nullptr;
+        ga.grad = d_grad; ga.contact = lik ? 1 : 0;
         rc = launch_gather(m, ga, R, st);
         if (rc) return rc;
     }
     if (d_energies) {
-        rc = launch_finalize(m, R, lik && need_forward, need_gather, d_energies, nullptr, st);
+        rc = launch_finalize(m, R, lik && need_forward, need_prior, false, d_energies, nullptr, st);
         if (rc) return rc;
     }
     return EHIC_OK;
@@ -383,8 +415,8 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
     if (!d_x || !d_p || !d_norm || !d_eps || !d_H) return fail(EHIC_ERR_INVALID, "null buffer");
     if (n_steps < 1) return fail(EHIC_ERR_INVALID, "n_steps must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
-    int terms = EHIC_TERM_ALL;
-    if (!m->dm.sphere_active) terms &= ~EHIC_TERM_SPHERE;
+    int prior_terms = EHIC_TERM_ALL & ~EHIC_TERM_LIKELIHOOD;
+    if (!m->dm.sphere_active) prior_terms &= ~EHIC_TERM_SPHERE;
     rc = launch_pack(m, R, d_x, m->xs[0], st);
     if (rc) return rc;
     int cur = 0;
@@ -393,16 +425,18 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
         const bool ends = first || last;
         rc = launch_forward(m, R, m->xs[cur], d_norm, nullptr, true, ends, st);
         if (rc) return rc;
+        rc = launch_prior(m, R, prior_terms, m->xs[cur], d_beta, true, ends, st);
+        if (rc) return rc;
         GatherArgs ga{};
-        ga.xs = m->xs[cur]; ga.wbuf = m->wbuf; ga.lammda = d_lammda; ga.beta = d_beta;
-        ga.grad = nullptr; ga.partB = ends ? m->partB : nullptr; ga.terms = terms;
+        ga.xs = m->xs[cur]; ga.wbuf = m->wbuf; ga.lammda = d_lammda; ga.gprior = m->gprior;
+        ga.grad = nullptr; ga.partK = ends ? m->partK : nullptr; ga.contact = 1;
         ga.p = d_p; ga.eps = d_eps; ga.kick = ends ? 0.5 : 1.0;
         ga.xs_next = last ? nullptr : m->xs[cur ^ 1];
-        ga.kinetic_before = first ? 1 : (last ? 2 : 0);
+        ga.kinetic_mode = first ? 1 : (last ? 2 : 0);
         rc = launch_gather(m, ga, R, st);
         if (rc) return rc;
         if (ends) {
-            rc = launch_finalize(m, R, true, true, m->energies, m->kinetic, st);
+            rc = launch_finalize(m, R, true, true, true, m->energies, m->kinetic, st);
             if (rc) return rc;
             hamiltonian_kernel<<<(R + 127) / 128, 128, 0, st>>>(m->energies, m->kinetic, d_lammda, d_beta, d_H, first ? 0 : 2, R);
             LAUNCHED();

@@ -11,13 +11,14 @@
 // N=2000, S=100: noise next to the pair arithmetic).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 #include <stdint.h>
 
 namespace ehic {
 
 struct DevModel {
     int N, S, Np, n_slices;
-    long long M, tot;
+    long long M, tot, wstride;   // wstride = tot + tail pad: per-replica stride of the weight buffer
     // pair view
     const int *pi, *pj, *slot_a, *slot_b;
     const double *pdc, *pcnt;
@@ -162,7 +163,7 @@ forward_kernel(DevModel dm, const double *__restrict__ xs, const double *__restr
         double em = __dsub_rn(1.0, __ddiv_rn(c, md));
         double w = __dmul_rn(__dmul_rn(__dmul_rn(0.5, em), nrm), alpha);
         if (wbuf) {
-            double *wr = wbuf + (long long)r * dm.tot;
+            double *wr = wbuf + (long long)r * dm.wstride;
             wr[dm.slot_a[m]] = w;
             wr[dm.slot_b[m]] = w;
         }
@@ -183,277 +184,333 @@ forward_kernel(DevModel dm, const double *__restrict__ xs, const double *__restr
 }
 
 // ---------------------------------------------------------------------------------------
-// Gather kernel: everything that produces a per-bead quantity.
+// Prior kernel (north-star kernel 2): repulsive nonbonded term as a tiled all-pairs gather,
+// with the backbone and sphere terms fused into the same pass.
 //
-// warp <-> (replica r, slice of 32 consecutive beads, tile of KT structures); lane <-> bead.
-//   1. contact term: walk the lane's row of the sliced-ELL row view, for each partner o and
-//      each of the KT structures recompute the pair (cheaper than storing [S][M] scratch as
-//      the reference does) and accumulate g_b += f * (x_o - x_b)       (likelihoods_c.pyx:62-73)
-//   2. nonbonded term: all beads o != b of the same structure, partner index uniform across
-//      the warp (broadcast loads), quartic repulsion                     (forcefield_c.pyx:33-59,
-//                                                                         c/prolsq.c:8-38)
-//   3. backbone (bonds b-1,b and b,b+1) and sphere terms              (backbone_prior_c.pyx:11-44,
-//                                                                         sphere_prior_c.pyx:12-38)
-//   4. epilogue: tempered sum written to grad[R][S][N][3]; optional leapfrog kick + drift
-//      (HMC trajectories keep x, p on the device); per-warp energy partials.
-// No atomics anywhere: every output element has exactly one writer and a fixed summation order.
+// thread <-> (replica r, structure k, bead b); a CTA is 256 consecutive beads of ONE structure.
+// Partner beads are staged through shared memory in tiles of 256 as (x, y), (z, radius) pairs
+// and read back with warp-uniform (broadcast) LDS.128.  Every pair is visited from both ends
+// (gather form): no atomics, fixed ascending-partner summation order -- the order in which
+// forcefield_c.pyx:47-57 accumulates into res[b].
+// Output: gprior[R][S][N][3] = beta * dE_nb/dx + d(-log p_bb)/dx + d(-log p_sphere)/dx and
+// per-CTA energy partials partP[(r*S+k)*gridDim.x + blockIdx.x][3] = (sum a^4, sum bb, sum sph).
+#define EHIC_PRIOR_THREADS 256
 
-struct GatherArgs {
-    const double *xs;       // [R][S][3][Np] positions the gradient is evaluated at
-    const double *wbuf;     // [R][tot] per-slot Poisson weights (from forward_kernel)
-    const double *lammda;   // [R] or NULL
-    const double *beta;     // [R] or NULL
-    double *grad;           // [R][S][N][3] or NULL
-    double *partB;          // [items][4] (a^4 sum, backbone E, sphere E, kinetic) or NULL
-    int terms;
-    // leapfrog epilogue (all NULL/0 outside HMC)
-    double *p;              // [R][S][N][3] momenta, updated in place:  p -= kick * eps * g
-    const double *eps;      // [R]
-    double kick;            // 0.5 or 1.0
-    double *xs_next;        // [R][S][3][Np]: xs + eps * p (after the kick), or NULL (no drift)
-    int kinetic_before;     // partB[3] = sum p^2 before the kick (1) / after the kick (2) / none (0)
-};
-
-template <bool EXACT, int KT>
-__global__ void __launch_bounds__(128)
-gather_kernel(DevModel dm, GatherArgs ga, int R, int nkt)
+template <bool EXACT>
+__global__ void __launch_bounds__(EHIC_PRIOR_THREADS)
+prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restrict__ beta,
+             double *__restrict__ gprior, double *__restrict__ partP, int terms, double r_max)
 {
-    const int lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long n_items = (long long)R * dm.n_slices * nkt;
-    if (item >= n_items) return;
-    const int kt = (int)(item % nkt);
-    const long long tmp = item / nkt;
-    const int sl = (int)(tmp % dm.n_slices);
-    const int r = (int)(tmp / dm.n_slices);
-    const int b = sl * 32 + lane;
+    const int k = blockIdx.y, r = blockIdx.z;
+    const int b = blockIdx.x * EHIC_PRIOR_THREADS + threadIdx.x;
     const bool bead_ok = b < dm.N;
-    const int bb = bead_ok ? b : dm.N - 1;           // clamped index for loads
+    const int bb = bead_ok ? b : dm.N - 1;
     const int Np = dm.Np;
-    const long long plane = 3LL * Np;
-    const int k0 = kt * KT;
-
-    const double *xk[KT];
-    bool k_ok[KT];
-    double xb[KT][3], gt[KT][3];
-#pragma unroll
-    for (int t = 0; t < KT; t++) {
-        int k = k0 + t;
-        k_ok[t] = k < dm.S;
-        if (k >= dm.S) k = dm.S - 1;
-        xk[t] = ga.xs + ((long long)r * dm.S + k) * plane;
-        xb[t][0] = xk[t][bb]; xb[t][1] = xk[t][Np + bb]; xb[t][2] = xk[t][2 * Np + bb];
-        gt[t][0] = gt[t][1] = gt[t][2] = 0.0;
-    }
-    const double lam = ga.lammda ? ga.lammda[r] : 1.0;
-    const double bet = ga.beta ? ga.beta[r] : 1.0;
+    const double *xk = xs + ((long long)r * dm.S + k) * 3LL * Np;
+    const double xb0 = xk[bb], xb1 = xk[Np + bb], xb2 = xk[2 * Np + bb];
+    const double rb = dm.radii[bb];
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
     double e_nb = 0.0, e_bb = 0.0, e_sp = 0.0;
-    const bool want_grad = (ga.grad != nullptr) || (ga.p != nullptr);
 
-    // ---- 1. contact term ----------------------------------------------------------------
-    if ((ga.terms & 1) && want_grad && dm.M > 0) {
-        double acc[KT][3];
-#pragma unroll
-        for (int t = 0; t < KT; t++) acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
-        const long long off = dm.slice_off[sl];
-        const int width = dm.slice_w[sl];
-        const int *ej = dm.ent_j + off + lane;
-        const double *edc = dm.ent_dc + off + lane;
-        const double *ew = ga.wbuf + (long long)r * dm.tot + off + lane;
-        const double alpha = dm.alpha;
-        const double aa = __dmul_rn(alpha, alpha);
-        for (int e = 0; e < width; e++) {
-            const int o = ej[32 * e];
-            if (o < 0) continue;
-            const double dc = edc[32 * e];
-            const double w = ew[32 * e];
-#pragma unroll
-            for (int t = 0; t < KT; t++) {
-                const double ox = xk[t][o], oy = xk[t][Np + o], oz = xk[t][2 * Np + o];
-                if (EXACT) {
-                    // likelihoods_c.pyx:64-73 with d, sqrtdenoms recomputed as in pxd:33-37
-                    double d0 = __dsub_rn(xb[t][0], ox), d1 = __dsub_rn(xb[t][1], oy), d2 = __dsub_rn(xb[t][2], oz);
-                    double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-                    double d = __dsqrt_rn(s);
-                    double u = __dsub_rn(dc, d);
-                    double g = __dadd_rn(1.0, __dmul_rn(__dmul_rn(aa, u), u));
-                    double q = __dsqrt_rn(g);
-                    double f = __ddiv_rn(w, __dmul_rn(__dmul_rn(g, q), d));
-                    acc[t][0] = __dadd_rn(acc[t][0], __dmul_rn(__dsub_rn(ox, xb[t][0]), f));
-                    acc[t][1] = __dadd_rn(acc[t][1], __dmul_rn(__dsub_rn(oy, xb[t][1]), f));
-                    acc[t][2] = __dadd_rn(acc[t][2], __dmul_rn(__dsub_rn(oz, xb[t][2]), f));
-                } else {
-                    double dx = ox - xb[t][0], dy = oy - xb[t][1], dz = oz - xb[t][2];
-                    double s = fma(dz, dz, fma(dy, dy, dx * dx));
-                    double rd = rsqrt_nr(s);
-                    double tt = alpha * (dc - s * rd);
-                    double rq = rsqrt_nr(fma(tt, tt, 1.0));
-                    double f = w * ((rq * rq) * (rq * rd));
-                    acc[t][0] = fma(f, dx, acc[t][0]);
-                    acc[t][1] = fma(f, dy, acc[t][1]);
-                    acc[t][2] = fma(f, dz, acc[t][2]);
-                }
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < KT; t++) {
-            gt[t][0] = __dmul_rn(lam, acc[t][0]);
-            gt[t][1] = __dmul_rn(lam, acc[t][1]);
-            gt[t][2] = __dmul_rn(lam, acc[t][2]);
-        }
-    }
-
-    // ---- 2. nonbonded term (tiled all-pairs gather) ---------------------------------------
-    if (ga.terms & 2) {
-        double acc[KT][3], ea[KT];
-#pragma unroll
-        for (int t = 0; t < KT; t++) { acc[t][0] = acc[t][1] = acc[t][2] = 0.0; ea[t] = 0.0; }
-        const double rb = dm.radii[bb];
+    if (terms & 2) {
+        __shared__ double2 sxy[EHIC_PRIOR_THREADS];
+        __shared__ double2 szr[EHIC_PRIOR_THREADS];
         const double rb2 = __dmul_rn(rb, rb);
-        for (int o = 0; o < dm.N; o++) {
-            const double ro = dm.radii[o];
-            // forcefield_c.pyx:50: d < radii2[i] + radii2[j] + 2 * radii[i] * radii[j]
-            const double lim = EXACT
-                ? __dadd_rn(__dadd_rn(rb2, __dmul_rn(ro, ro)), __dmul_rn(__dmul_rn(2.0, rb), ro))
-                : (rb + ro) * (rb + ro);
-            const double d0sum = __dadd_rn(rb, ro);
-#pragma unroll
-            for (int t = 0; t < KT; t++) {
-                const double ox = xk[t][o], oy = xk[t][Np + o], oz = xk[t][2 * Np + o];
+        const double coarse = (rb + r_max) * (rb + r_max);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int t0 = 0; t0 < dm.N; t0 += EHIC_PRIOR_THREADS) {
+            __syncthreads();
+            {
+                int o = t0 + threadIdx.x;
+                int oo = o < dm.N ? o : dm.N - 1;
+                sxy[threadIdx.x] = make_double2(xk[oo], xk[Np + oo]);
+                szr[threadIdx.x] = make_double2(xk[2 * Np + oo], dm.radii[oo]);
+            }
+            __syncthreads();
+            const int cnt = min(EHIC_PRIOR_THREADS, dm.N - t0);
+#pragma unroll 4
+            for (int q = 0; q < cnt; q++) {
+                const double2 pxy = sxy[q], pzr = szr[q];
+                const int o = t0 + q;
                 if (EXACT) {
-                    double d0 = __dsub_rn(xb[t][0], ox), d1 = __dsub_rn(xb[t][1], oy), d2 = __dsub_rn(xb[t][2], oz);
+                    double d0 = __dsub_rn(xb0, pxy.x), d1 = __dsub_rn(xb1, pxy.y), d2 = __dsub_rn(xb2, pzr.x);
                     double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+                    const double ro = pzr.y;
+                    // forcefield_c.pyx:50: d < radii2[i] + radii2[j] + 2 * radii[i] * radii[j]
+                    double lim = __dadd_rn(__dadd_rn(rb2, __dmul_rn(ro, ro)), __dmul_rn(__dmul_rn(2.0, rb), ro));
                     if (s < lim && o != b) {
                         double d = __dsqrt_rn(s);
-                        double a = __dsub_rn(d0sum, d);
+                        double a = __dsub_rn(__dadd_rn(rb, ro), d);
                         double g = __ddiv_rn(__dmul_rn(__dmul_rn(a, a), a), d);
-                        acc[t][0] = __dadd_rn(acc[t][0], __dmul_rn(__dsub_rn(ox, xb[t][0]), g));
-                        acc[t][1] = __dadd_rn(acc[t][1], __dmul_rn(__dsub_rn(oy, xb[t][1]), g));
-                        acc[t][2] = __dadd_rn(acc[t][2], __dmul_rn(__dsub_rn(oz, xb[t][2]), g));
-                        double a2 = a * a;
-                        ea[t] += a2 * a2;
+                        a0 = __dadd_rn(a0, __dmul_rn(__dsub_rn(pxy.x, xb0), g));
+                        a1 = __dadd_rn(a1, __dmul_rn(__dsub_rn(pxy.y, xb1), g));
+                        a2 = __dadd_rn(a2, __dmul_rn(__dsub_rn(pzr.x, xb2), g));
+                        double aa = a * a;
+                        e_nb += aa * aa;
                     }
                 } else {
-                    double dx = ox - xb[t][0], dy = oy - xb[t][1], dz = oz - xb[t][2];
+                    double dx = pxy.x - xb0, dy = pxy.y - xb1, dz = pzr.x - xb2;
                     double s = fma(dz, dz, fma(dy, dy, dx * dx));
-                    if (s < lim && o != b) {
-                        double rd = rsqrt_nr(s);
-                        double a = d0sum - s * rd;
-                        double a2 = a * a;
-                        double g = a2 * a * rd;
-                        acc[t][0] = fma(g, dx, acc[t][0]);
-                        acc[t][1] = fma(g, dy, acc[t][1]);
-                        acc[t][2] = fma(g, dz, acc[t][2]);
-                        ea[t] += a2 * a2;
+                    if (s < coarse && o != b) {
+                        double d0s = rb + pzr.y;
+                        if (s < d0s * d0s) {
+                            double rd = rsqrt_nr(s);
+                            double a = d0s - s * rd;
+                            double aa = a * a;
+                            double g = aa * a * rd;
+                            a0 = fma(g, dx, a0); a1 = fma(g, dy, a1); a2 = fma(g, dz, a2);
+                            e_nb += aa * aa;
+                        }
                     }
                 }
             }
         }
         // forcefield_c.pyx:59: force_constant * 2.0 * res ; nonbonded_prior.py:119-121: * beta
         const double k2 = __dmul_rn(dm.k_nb, 2.0);
-#pragma unroll
-        for (int t = 0; t < KT; t++) {
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                gt[t][c] = __dadd_rn(gt[t][c], __dmul_rn(bet, __dmul_rn(k2, acc[t][c])));
-            if (k_ok[t] && bead_ok) e_nb += ea[t];
-        }
+        const double bet = beta ? beta[r] : 1.0;
+        g0 = __dmul_rn(bet, __dmul_rn(k2, a0));
+        g1 = __dmul_rn(bet, __dmul_rn(k2, a1));
+        g2 = __dmul_rn(bet, __dmul_rn(k2, a2));
     }
 
-    // ---- 3a. backbone: bonds (b-1, b) then (b, b+1), the reference's visiting order --------
-    if (ga.terms & 4) {
-        const double kbb = dm.k_bb;
-        const bool has_prev = b > 0 && bead_ok && !isinf(dm.bb_ul[b - 1]);
+    // backbone: bonds (b-1, b) then (b, b+1), the reference's visiting order (backbone_prior_c.pyx:26-42)
+    if (terms & 4) {
+        const bool has_prev = bead_ok && b > 0 && !isinf(dm.bb_ul[b - 1]);
         const bool has_next = bead_ok && !isinf(dm.bb_ul[bb]);
-        const double ulp = has_prev ? dm.bb_ul[b - 1] : 0.0, llp = has_prev ? dm.bb_ll[b - 1] : 0.0;
-        const double uln = has_next ? dm.bb_ul[bb] : 0.0, lln = has_next ? dm.bb_ll[bb] : 0.0;
-#pragma unroll
-        for (int t = 0; t < KT; t++) {
-            double res[3] = {0.0, 0.0, 0.0};
-            if (has_prev) {   // i = b, i-1 = b-1 (backbone_prior_c.pyx:26-42)
-                double d0 = __dsub_rn(xb[t][0], xk[t][b - 1]);
-                double d1 = __dsub_rn(xb[t][1], xk[t][Np + b - 1]);
-                double d2 = __dsub_rn(xb[t][2], xk[t][2 * Np + b - 1]);
-                double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-                if (s > __dmul_rn(ulp, ulp)) {
-                    double d = __dsqrt_rn(s), a = __dsub_rn(d, ulp);
-                    res[0] = __ddiv_rn(__dmul_rn(a, d0), d);
-                    res[1] = __ddiv_rn(__dmul_rn(a, d1), d);
-                    res[2] = __ddiv_rn(__dmul_rn(a, d2), d);
-                    if (k_ok[t]) e_bb += a * a;
-                } else if (s < __dmul_rn(llp, llp)) {
-                    double d = __dsqrt_rn(s), a = __dsub_rn(llp, d);
-                    res[0] = -__ddiv_rn(__dmul_rn(a, d0), d);
-                    res[1] = -__ddiv_rn(__dmul_rn(a, d1), d);
-                    res[2] = -__ddiv_rn(__dmul_rn(a, d2), d);
-                    if (k_ok[t]) e_bb += a * a;
-                }
+        double res0 = 0.0, res1 = 0.0, res2 = 0.0;
+        if (has_prev) {   // i = b, i-1 = b-1
+            const double ul = dm.bb_ul[b - 1], ll = dm.bb_ll[b - 1];
+            double d0 = __dsub_rn(xb0, xk[b - 1]), d1 = __dsub_rn(xb1, xk[Np + b - 1]), d2 = __dsub_rn(xb2, xk[2 * Np + b - 1]);
+            double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+            if (s > __dmul_rn(ul, ul)) {
+                double d = __dsqrt_rn(s), a = __dsub_rn(d, ul);
+                res0 = __ddiv_rn(__dmul_rn(a, d0), d); res1 = __ddiv_rn(__dmul_rn(a, d1), d); res2 = __ddiv_rn(__dmul_rn(a, d2), d);
+                e_bb += a * a;
+            } else if (s < __dmul_rn(ll, ll)) {
+                double d = __dsqrt_rn(s), a = __dsub_rn(ll, d);
+                res0 = -__ddiv_rn(__dmul_rn(a, d0), d); res1 = -__ddiv_rn(__dmul_rn(a, d1), d); res2 = -__ddiv_rn(__dmul_rn(a, d2), d);
+                e_bb += a * a;
             }
-            if (has_next) {   // i = b+1, i-1 = b
-                double d0 = __dsub_rn(xk[t][b + 1], xb[t][0]);
-                double d1 = __dsub_rn(xk[t][Np + b + 1], xb[t][1]);
-                double d2 = __dsub_rn(xk[t][2 * Np + b + 1], xb[t][2]);
-                double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-                if (s > __dmul_rn(uln, uln)) {
-                    double d = __dsqrt_rn(s), a = __dsub_rn(d, uln);
-                    res[0] = __dsub_rn(res[0], __ddiv_rn(__dmul_rn(a, d0), d));
-                    res[1] = __dsub_rn(res[1], __ddiv_rn(__dmul_rn(a, d1), d));
-                    res[2] = __dsub_rn(res[2], __ddiv_rn(__dmul_rn(a, d2), d));
-                } else if (s < __dmul_rn(lln, lln)) {
-                    double d = __dsqrt_rn(s), a = __dsub_rn(lln, d);
-                    res[0] = __dadd_rn(res[0], __ddiv_rn(__dmul_rn(a, d0), d));
-                    res[1] = __dadd_rn(res[1], __ddiv_rn(__dmul_rn(a, d1), d));
-                    res[2] = __dadd_rn(res[2], __ddiv_rn(__dmul_rn(a, d2), d));
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 3; c++) gt[t][c] = __dadd_rn(gt[t][c], __dmul_rn(kbb, res[c]));
         }
+        if (has_next) {   // i = b+1, i-1 = b
+            const double ul = dm.bb_ul[bb], ll = dm.bb_ll[bb];
+            double d0 = __dsub_rn(xk[b + 1], xb0), d1 = __dsub_rn(xk[Np + b + 1], xb1), d2 = __dsub_rn(xk[2 * Np + b + 1], xb2);
+            double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+            if (s > __dmul_rn(ul, ul)) {
+                double d = __dsqrt_rn(s), a = __dsub_rn(d, ul);
+                res0 = __dsub_rn(res0, __ddiv_rn(__dmul_rn(a, d0), d));
+                res1 = __dsub_rn(res1, __ddiv_rn(__dmul_rn(a, d1), d));
+                res2 = __dsub_rn(res2, __ddiv_rn(__dmul_rn(a, d2), d));
+            } else if (s < __dmul_rn(ll, ll)) {
+                double d = __dsqrt_rn(s), a = __dsub_rn(ll, d);
+                res0 = __dadd_rn(res0, __ddiv_rn(__dmul_rn(a, d0), d));
+                res1 = __dadd_rn(res1, __ddiv_rn(__dmul_rn(a, d1), d));
+                res2 = __dadd_rn(res2, __ddiv_rn(__dmul_rn(a, d2), d));
+            }
+        }
+        g0 = __dadd_rn(g0, __dmul_rn(dm.k_bb, res0));
+        g1 = __dadd_rn(g1, __dmul_rn(dm.k_bb, res1));
+        g2 = __dadd_rn(g2, __dmul_rn(dm.k_bb, res2));
     }
 
-    // ---- 3b. sphere (sphere_prior_c.pyx:25-36) ---------------------------------------------
-    if ((ga.terms & 8) && dm.sphere_active) {
-        const double rb = dm.radii[bb];
+    // sphere (sphere_prior_c.pyx:25-36)
+    if ((terms & 8) && dm.sphere_active) {
         const double R0 = dm.sph_R;
         // radius2 + bead_radii2[i] - 2 * radius * bead_radii[i]
-        const double lim = __dsub_rn(__dadd_rn(__dmul_rn(R0, R0), __dmul_rn(rb, rb)),
-                                     __dmul_rn(__dmul_rn(2.0, R0), rb));
-#pragma unroll
-        for (int t = 0; t < KT; t++) {
-            double d0 = __dsub_rn(xb[t][0], dm.sph_cx), d1 = __dsub_rn(xb[t][1], dm.sph_cy),
-                   d2 = __dsub_rn(xb[t][2], dm.sph_cz);
-            double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-            if (!(s < lim)) {
-                double d = __dsqrt_rn(s);
-                double a = __dsub_rn(__dadd_rn(d, rb), R0);
-                double f = __ddiv_rn(a, d);
-                gt[t][0] = __dadd_rn(gt[t][0], __dmul_rn(dm.sph_k, __dmul_rn(d0, f)));
-                gt[t][1] = __dadd_rn(gt[t][1], __dmul_rn(dm.sph_k, __dmul_rn(d1, f)));
-                gt[t][2] = __dadd_rn(gt[t][2], __dmul_rn(dm.sph_k, __dmul_rn(d2, f)));
-                // sphere_prior.py:70-72 penalises d + r > R only
-                if (k_ok[t] && bead_ok && a > 0.0) e_sp += a * a;
-            }
+        const double lim = __dsub_rn(__dadd_rn(__dmul_rn(R0, R0), __dmul_rn(rb, rb)), __dmul_rn(__dmul_rn(2.0, R0), rb));
+        double d0 = __dsub_rn(xb0, dm.sph_cx), d1 = __dsub_rn(xb1, dm.sph_cy), d2 = __dsub_rn(xb2, dm.sph_cz);
+        double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+        if (!(s < lim)) {
+            double d = __dsqrt_rn(s);
+            double a = __dsub_rn(__dadd_rn(d, rb), R0);
+            double f = __ddiv_rn(a, d);
+            g0 = __dadd_rn(g0, __dmul_rn(dm.sph_k, __dmul_rn(d0, f)));
+            g1 = __dadd_rn(g1, __dmul_rn(dm.sph_k, __dmul_rn(d1, f)));
+            g2 = __dadd_rn(g2, __dmul_rn(dm.sph_k, __dmul_rn(d2, f)));
+            if (a > 0.0) e_sp += a * a;      // sphere_prior.py:70-72 penalises d + r > R only
         }
     }
 
-    // ---- 4. epilogue ----------------------------------------------------------------------
+    if (bead_ok && gprior) {
+        const long long at = (((long long)r * dm.S + k) * dm.N + b) * 3;
+        gprior[at] = g0; gprior[at + 1] = g1; gprior[at + 2] = g2;
+    }
+    if (partP) {
+        __shared__ double sh[3][EHIC_PRIOR_THREADS / 32];
+        if (!bead_ok) { e_nb = 0.0; e_bb = 0.0; e_sp = 0.0; }
+        e_nb = warp_sum(e_nb); e_bb = warp_sum(e_bb); e_sp = warp_sum(e_sp);
+        if ((threadIdx.x & 31) == 0) {
+            sh[0][threadIdx.x >> 5] = e_nb; sh[1][threadIdx.x >> 5] = e_bb; sh[2][threadIdx.x >> 5] = e_sp;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+            for (int q = 0; q < EHIC_PRIOR_THREADS / 32; q++) { t0 += sh[0][q]; t1 += sh[1][q]; t2 += sh[2][q]; }
+            double *o = partP + (((long long)r * dm.S + k) * gridDim.x + blockIdx.x) * 3;
+            o[0] = t0; o[1] = t1; o[2] = t2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Gather kernel (second half of north-star kernel 1 + the leapfrog epilogue of kernel 3).
+//
+// CTA <-> (replica r, slice of 32 consecutive beads, group of 4 structure tiles);
+// warp <-> one tile of KT structures; lane <-> bead.
+// The slice's rows of the sliced-ELL row view (partner index, contact distance, Poisson
+// weight: 20 B per entry per lane) are streamed ONCE per CTA through a 3-stage cp.async
+// shared-memory ring and shared by the 4 warps; partner coordinates are gathered from the
+// SoA working copy (L1/L2 resident: 48 KB per structure at N=2000).  Each pair is recomputed
+// from coordinates instead of being read back from [S][M] scratch as the reference does
+// (likelihoods_c.pyx:36-43, 3.2 GB at config D).
+//   g_b += f * (x_o - x_b),  f = w_m / (g q d)                          (likelihoods_c.pyx:62-73)
+// Epilogue: grad = lammda * g + gprior; optional leapfrog kick + drift (HMC trajectories keep
+// x and p on the device) and kinetic-energy partials.
+// No atomics anywhere: every output element has exactly one writer and a fixed summation order.
+#define EHIC_GATHER_WARPS 4
+#define EHIC_CHUNK 16      // row entries per pipeline stage
+#define EHIC_STAGES 3
+
+struct GatherArgs {
+    const double *xs;       // [R][S][3][Np] positions the gradient is evaluated at
+    const double *wbuf;     // [R][tot+pad] per-slot Poisson weights (from forward_kernel)
+    const double *lammda;   // [R] or NULL
+    const double *gprior;   // [R][S][N][3] or NULL
+    double *grad;           // [R][S][N][3] or NULL
+    double *partK;          // [items] kinetic partials or NULL
+    int contact;            // evaluate the contact term
+    // leapfrog epilogue (all NULL/0 outside HMC)
+    double *p;              // [R][S][N][3] momenta, updated in place:  p -= kick * eps * g
+    const double *eps;      // [R]
+    double kick;            // 0.5 or 1.0
+    double *xs_next;        // [R][S][3][Np]: xs + eps * p (after the kick), or NULL (no drift)
+    int kinetic_mode;       // partK = sum p^2 before the kick (1) / after the kick (2) / none (0)
+};
+
+template <bool EXACT, int KT>
+__global__ void __launch_bounds__(EHIC_GATHER_WARPS * 32)
+gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
+{
+    __shared__ __align__(16) int s_o[EHIC_STAGES][EHIC_CHUNK * 32];
+    __shared__ __align__(16) double s_dc[EHIC_STAGES][EHIC_CHUNK * 32];
+    __shared__ __align__(16) double s_w[EHIC_STAGES][EHIC_CHUNK * 32];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ktg = blockIdx.x % nktg;
+    const int tmp = blockIdx.x / nktg;
+    const int sl = tmp % dm.n_slices;
+    const int r = tmp / dm.n_slices;
+    const int kt = ktg * EHIC_GATHER_WARPS + warp;
+    const bool kt_ok = kt < nkt;
+    const int b = sl * 32 + lane;
+    const bool bead_ok = b < dm.N;
+    const int bb = bead_ok ? b : dm.N - 1;
+    const int Np = dm.Np;
+    const long long plane = 3LL * Np;
+    const int k0 = (kt_ok ? kt : 0) * KT;
+
+    const double *xk[KT];
+    bool k_ok[KT];
+    double xb[KT][3], acc[KT][3];
+#pragma unroll
+    for (int t = 0; t < KT; t++) {
+        int k = k0 + t;
+        k_ok[t] = kt_ok && k < dm.S;
+        if (k >= dm.S) k = dm.S - 1;
+        xk[t] = ga.xs + ((long long)r * dm.S + k) * plane;
+        xb[t][0] = xk[t][bb]; xb[t][1] = xk[t][Np + bb]; xb[t][2] = xk[t][2 * Np + bb];
+        acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
+    }
+
+    if (ga.contact && dm.M > 0) {
+        const long long off = dm.slice_off[sl];
+        const int width = dm.slice_w[sl];
+        const int nchunks = (width + EHIC_CHUNK - 1) / EHIC_CHUNK;
+        const int *gj = dm.ent_j + off;
+        const double *gdc = dm.ent_dc + off;
+        const double *gw = ga.wbuf + (long long)r * dm.wstride + off;
+        const double alpha = dm.alpha;
+        const double aa = __dmul_rn(alpha, alpha);
+        const int tid = threadIdx.x;
+        auto issue = [&](int c) {
+            if (c < nchunks) {
+                const int st = c % EHIC_STAGES;
+                const long long base = (long long)c * EHIC_CHUNK * 32;
+                __pipeline_memcpy_async(&s_o[st][tid * 4], gj + base + tid * 4, 16);
+                __pipeline_memcpy_async(&s_dc[st][tid * 2], gdc + base + tid * 2, 16);
+                __pipeline_memcpy_async(&s_dc[st][256 + tid * 2], gdc + base + 256 + tid * 2, 16);
+                __pipeline_memcpy_async(&s_w[st][tid * 2], gw + base + tid * 2, 16);
+                __pipeline_memcpy_async(&s_w[st][256 + tid * 2], gw + base + 256 + tid * 2, 16);
+            }
+            __pipeline_commit();
+        };
+#pragma unroll
+        for (int c = 0; c < EHIC_STAGES - 1; c++) issue(c);
+        for (int c = 0; c < nchunks; c++) {
+            __pipeline_wait_prior(EHIC_STAGES - 2);
+            __syncthreads();                       // chunk c visible; everyone is done with chunk c-1
+            issue(c + EHIC_STAGES - 1);
+            const int st = c % EHIC_STAGES;
+            const int cnt = min(EHIC_CHUNK, width - c * EHIC_CHUNK);
+#pragma unroll 2
+            for (int e = 0; e < cnt; e++) {
+                const int o = s_o[st][e * 32 + lane];
+                const double dc = s_dc[st][e * 32 + lane];
+                const double w = s_w[st][e * 32 + lane];
+#pragma unroll
+                for (int t = 0; t < KT; t++) {
+                    const double ox = xk[t][o], oy = xk[t][Np + o], oz = xk[t][2 * Np + o];
+                    if (EXACT) {
+                        // likelihoods_c.pyx:64-73 with d, sqrtdenoms recomputed as in pxd:33-37
+                        double d0 = __dsub_rn(xb[t][0], ox), d1 = __dsub_rn(xb[t][1], oy), d2 = __dsub_rn(xb[t][2], oz);
+                        double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+                        double d = __dsqrt_rn(s);
+                        double u = __dsub_rn(dc, d);
+                        double g = __dadd_rn(1.0, __dmul_rn(__dmul_rn(aa, u), u));
+                        double q = __dsqrt_rn(g);
+                        double f = __ddiv_rn(w, __dmul_rn(__dmul_rn(g, q), d));
+                        acc[t][0] = __dadd_rn(acc[t][0], __dmul_rn(__dsub_rn(ox, xb[t][0]), f));
+                        acc[t][1] = __dadd_rn(acc[t][1], __dmul_rn(__dsub_rn(oy, xb[t][1]), f));
+                        acc[t][2] = __dadd_rn(acc[t][2], __dmul_rn(__dsub_rn(oz, xb[t][2]), f));
+                    } else {
+                        double dx = ox - xb[t][0], dy = oy - xb[t][1], dz = oz - xb[t][2];
+                        double s = fma(dz, dz, fma(dy, dy, dx * dx));
+                        double rd = rsqrt_nr(s);
+                        double tt = alpha * (dc - s * rd);
+                        double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                        double f = w * ((rq * rq) * (rq * rd));
+                        acc[t][0] = fma(f, dx, acc[t][0]);
+                        acc[t][1] = fma(f, dy, acc[t][1]);
+                        acc[t][2] = fma(f, dz, acc[t][2]);
+                    }
+                }
+            }
+        }
+        __pipeline_wait_prior(0);
+    }
+
+    // ---- epilogue -------------------------------------------------------------------------
+    const double lam = ga.lammda ? ga.lammda[r] : 1.0;
     double kin = 0.0;
 #pragma unroll
     for (int t = 0; t < KT; t++) {
         if (!(k_ok[t] && bead_ok)) continue;
         const int k = k0 + t;
         const long long at = (((long long)r * dm.S + k) * dm.N + b) * 3;
-        if (ga.grad) {
-            ga.grad[at] = gt[t][0]; ga.grad[at + 1] = gt[t][1]; ga.grad[at + 2] = gt[t][2];
+        double g0 = __dmul_rn(lam, acc[t][0]), g1 = __dmul_rn(lam, acc[t][1]), g2 = __dmul_rn(lam, acc[t][2]);
+        if (ga.gprior) {
+            g0 = __dadd_rn(g0, ga.gprior[at]); g1 = __dadd_rn(g1, ga.gprior[at + 1]); g2 = __dadd_rn(g2, ga.gprior[at + 2]);
         }
+        if (ga.grad) { ga.grad[at] = g0; ga.grad[at + 1] = g1; ga.grad[at + 2] = g2; }
         if (ga.p) {
             const double eps = ga.eps[r];
             double p0 = ga.p[at], p1 = ga.p[at + 1], p2 = ga.p[at + 2];
-            if (ga.kinetic_before == 1) kin += p0 * p0 + p1 * p1 + p2 * p2;
+            if (ga.kinetic_mode == 1) kin += p0 * p0 + p1 * p1 + p2 * p2;
             const double ke = ga.kick * eps;
-            p0 = fma(-ke, gt[t][0], p0); p1 = fma(-ke, gt[t][1], p1); p2 = fma(-ke, gt[t][2], p2);
+            p0 = fma(-ke, g0, p0); p1 = fma(-ke, g1, p1); p2 = fma(-ke, g2, p2);
             ga.p[at] = p0; ga.p[at + 1] = p1; ga.p[at + 2] = p2;
-            if (ga.kinetic_before == 2) kin += p0 * p0 + p1 * p1 + p2 * p2;
+            if (ga.kinetic_mode == 2) kin += p0 * p0 + p1 * p1 + p2 * p2;
             if (ga.xs_next) {
                 double *xn = ga.xs_next + ((long long)r * dm.S + k) * plane;
                 xn[b] = fma(eps, p0, xb[t][0]);
@@ -462,20 +519,18 @@ gather_kernel(DevModel dm, GatherArgs ga, int R, int nkt)
             }
         }
     }
-    if (ga.partB) {
-        e_nb = warp_sum(e_nb); e_bb = warp_sum(e_bb); e_sp = warp_sum(e_sp); kin = warp_sum(kin);
-        if (lane == 0) {
-            double *o = ga.partB + item * 4;
-            o[0] = e_nb; o[1] = e_bb; o[2] = e_sp; o[3] = kin;
-        }
+    if (ga.partK) {
+        kin = warp_sum(kin);
+        if (lane == 0) ga.partK[(long long)blockIdx.x * EHIC_GATHER_WARPS + warp] = kin;
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// Fixed-order reduction of the per-block / per-warp partials into E[R][4] (+ H[R][.]).
+// Fixed-order reduction of the per-block / per-warp partials into E[R][4] and K[R].
 __global__ void __launch_bounds__(256)
 finalize_kernel(DevModel dm, const double *__restrict__ partA, int nA,
-                const double *__restrict__ partB, long long itemsB_per_replica,
+                const double *__restrict__ partP, long long nP,
+                const double *__restrict__ partK, long long nK,
                 double *__restrict__ energies, double *__restrict__ kinetic)
 {
     const int r = blockIdx.x;
@@ -483,11 +538,13 @@ finalize_kernel(DevModel dm, const double *__restrict__ partA, int nA,
     double a = 0.0, e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
     if (partA)
         for (int q = threadIdx.x; q < nA; q += 256) a += partA[(long long)r * nA + q];
-    if (partB)
-        for (long long q = threadIdx.x; q < itemsB_per_replica; q += 256) {
-            const double *o = partB + ((long long)r * itemsB_per_replica + q) * 4;
-            e0 += o[0]; e1 += o[1]; e2 += o[2]; e3 += o[3];
+    if (partP)
+        for (long long q = threadIdx.x; q < nP; q += 256) {
+            const double *o = partP + ((long long)r * nP + q) * 3;
+            e0 += o[0]; e1 += o[1]; e2 += o[2];
         }
+    if (partK)
+        for (long long q = threadIdx.x; q < nK; q += 256) e3 += partK[(long long)r * nK + q];
     sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = e0; sh[2][threadIdx.x] = e1;
     sh[3][threadIdx.x] = e2; sh[4][threadIdx.x] = e3;
     __syncthreads();

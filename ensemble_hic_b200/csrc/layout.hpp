@@ -38,9 +38,10 @@ struct ContactLayout {
     std::vector<int64_t> slice_off;   // n_slices + 1, in entries
     std::vector<int32_t> slice_w;     // n_slices
     std::vector<int32_t> row_len;     // N
-    std::vector<int32_t> ent_j;       // tot, -1 = padding
-    std::vector<double> ent_dc;       // tot
-    int64_t tot = 0;
+    std::vector<int32_t> ent_j;       // tot + kTailPad; padding slots hold a harmless partner (weight 0)
+    std::vector<double> ent_dc;       // tot + kTailPad
+    int64_t tot = 0;                  // slots that belong to slices (multiple of 32)
+    static constexpr int64_t kTailPad = 16 * 32;   // so a 16-entry chunk copy never leaves the array
 };
 
 // Returns "" on success, otherwise an error message.
@@ -88,8 +89,18 @@ inline std::string build_layout(int32_t N, int64_t M, const int64_t *data, const
     }
     L.tot = L.slice_off[L.n_slices];
     if (L.tot >= ((int64_t)1 << 31)) return "contact list too large for 32-bit row slots";
-    L.ent_j.assign(L.tot, -1);
-    if (want_values) L.ent_dc.assign(L.tot, 0.0);
+    // Padding slots (rows shorter than the slice width, lanes past the last bead, tail) point at
+    // a real neighbouring bead and carry weight 0 / contact distance 0: the kernel needs no
+    // branch, and a zero weight contributes exactly 0 to the gradient.
+    L.ent_j.assign(L.tot + ContactLayout::kTailPad, 0);
+    for (int32_t sl = 0; sl < L.n_slices; sl++)
+        for (int32_t e = 0; e < L.slice_w[sl]; e++)
+            for (int32_t lane = 0; lane < 32; lane++) {
+                int32_t b = sl * 32 + lane;
+                int32_t pad = (b >= N) ? 0 : (b + 1 < N ? b + 1 : (b > 0 ? b - 1 : 0));
+                L.ent_j[L.slice_off[sl] + (int64_t)32 * e + lane] = pad;
+            }
+    if (want_values) L.ent_dc.assign(L.tot + ContactLayout::kTailPad, 0.0);
     L.slot_a.resize(M); L.slot_b.resize(M);
     std::vector<int32_t> fill(N, 0);
     auto place = [&](int32_t b, int32_t o, int64_t s, bool first) {

@@ -2,7 +2,8 @@
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from tests.helpers import random_walk
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from helpers import random_walk
 from ensemble_hic_b200.engine import Model, fma_peak, launch_count
 
 def main():
