@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- posterior gradient evaluations / s of the ensemble_hic hot path on B200.
+
+Contract (see the task statement): ``python bench.py --gpus N --steps K --warmup W``;
+for N > 1 it is launched under ``torch.distributed.run`` (one rank per GPU, NCCL).
+Prints ONE JSON line on rank 0.
+
+Workload (BASELINE.json configs[3], SURVEY.md 8d "D"): synthetic chain, 2000 beads x 100
+structures, dense contact list |i-j| > 1 (M = 1 997 001), 64 replicas over 8 GPUs
+= 8 replicas per GPU (weak scaling: per-GPU work is fixed).  One *step* = one posterior
+gradient evaluation (likelihood + nonbonded + backbone, the config has no sphere) of every
+replica resident on the GPU, batched in one C-ABI call.  value = replicas * steps / time.
+
+``--impl reference`` times the reference's own CPU kernels (oracle/_ref: the unmodified
+Cython of /root/reference compiled for CPython 3; the neighbour-list forcefield through the
+plain-C restatement because the reference's Python-2 C extension cannot be built) on a
+bounded sample of the same workload with all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BEADS, N_STRUCT, REPLICAS_PER_GPU = 2000, 100, 8
+RADIUS, CD_FACTOR, ALPHA, K_NB, K_BB = 0.5, 1.25, 10.0, 500.0, 500.0
+METRIC = "posterior_grad_evals_per_s"
+UNIT = "grad evals/s"
+
+# ALGORITHMIC flop per unit (sqrt and div count 1 flop each)
+FLOP_FWD_PER_PAIR = 22.0        # forward model, per (structure, data point)
+FLOP_BWD_PER_PAIR = 23.0        # likelihood gradient, per (structure, data point)
+FLOP_NB_PER_TEST = 9.0          # nonbonded, per tested pair i<j
+
+
+def problem(seed, n_replicas, N=N_BEADS, S=N_STRUCT):
+    """Seeded synthetic inputs of config D (counts are drawn on the fly from the forward model)."""
+    rng = np.random.default_rng(seed)
+    i, j = np.triu_indices(N, 2)
+    radii = np.full(N, RADIUS)
+    cds = (radii[i] + radii[j]) * CD_FACTOR                # = 1.25 for r = 0.5
+    d = rng.normal(size=(n_replicas, S, N, 3))
+    d /= np.linalg.norm(d, axis=3, keepdims=True)
+    X = np.cumsum(d * (1.8 * RADIUS), axis=2)               # random-walk chains, step 1.8 r
+    return dict(N=N, S=S, i=i, j=j, radii=radii, cds=cds, X=X, rng=rng)
+
+
+def ladder(n_total):
+    """lammda = beta, geometric-ish 1e-6 .. 1 (setup_functions.expspace shape)."""
+    a, n = 0.1, np.arange(1, n_total + 1)
+    g = (1.0 - 1e-6) / (np.exp(a * (n_total - 1.0)) - 1.0) * (np.exp(a * (n - 1.0)) - 1.0) + 1e-6
+    return g
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.p = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+
+def _cpu_worker(args):
+    seed, S_sample = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle.oracle import OraclePosterior, load_ref
+    pb = problem(seed, 1, S=S_sample)
+    M = len(pb["i"])
+    counts = pb["rng"].poisson(2.0, size=M)
+    data = np.ascontiguousarray(np.stack([pb["i"], pb["j"], counts], 1).astype(np.int64))
+    ul = pb["radii"][:-1] + pb["radii"][1:]
+    op = OraclePosterior(S_sample, data, pb["cds"], ALPHA, pb["radii"], K_NB, K_BB,
+                         [np.zeros(pb["N"] - 1)], [ul], [0, pb["N"]], kernels=load_ref(), nonbonded="nbl")
+    x = pb["X"][0].ravel()
+    t0 = time.perf_counter()
+    # the reference's call sequence per posterior gradient: calculate_gradient;
+    # per structure nonbonded energy (unused) + gradient, each rebuilding the list; backbone
+    for xk in x.reshape(S_sample, -1, 3):
+        op.nb_energy(xk)
+    g = op.gradient(x, 3.0, 1.0, 1.0)
+    dt = time.perf_counter() - t0
+    return dt, float(np.abs(g).max())
+
+
+def cpu_reference_rate(budget_s=20.0, cores=None):
+    """grad evals/s of the reference CPU kernels on the host cores, on a bounded sample."""
+    import multiprocessing as mp
+    from oracle import build_ref
+    from oracle.oracle import build_c_oracle, load_ref
+    build_c_oracle()
+    build_ref.build(verbose=False)
+    kind = "reference" if load_ref() is not None else "port"
+    cores = cores or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
+    try:
+        import psutil
+        free_gb = psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        free_gb = 32.0
+    # the reference allocates 2 x S x M doubles of scratch per call (likelihoods_c.pyx:36-43)
+    S_sample = N_STRUCT
+    per_s = 0.11                                    # ~ seconds of one core per structure (probe)
+    while S_sample > 5 and (S_sample * per_s > budget_s or cores * S_sample * 0.04 > 0.6 * free_gb):
+        S_sample //= 2
+    ctx = mp.get_context("spawn")      # the parent may hold a CUDA context: never fork it
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(1000 + c, S_sample) for c in range(cores)])
+    wall = max(r[0] for r in res)
+    # cost is linear in the number of structures: scale the sample to a full S = 100 gradient
+    rate = cores / (wall * N_STRUCT / S_sample)
+    sample = ("one posterior gradient per core at N=%d, M=%d, S_sample=%d of %d structures "
+              "(cost linear in S, scaled by %d/%d); %d worker processes; %s kernels%s"
+              % (N_BEADS, len(np.triu_indices(N_BEADS, 2)[0]), S_sample, N_STRUCT, N_STRUCT, S_sample, cores,
+                 "reference Cython (oracle/_ref)" if kind == "reference" else "C oracle port",
+                 ", neighbour-list forcefield via C restatement"))
+    return rate, cores, kind, sample, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    rates, last = [], None
+    for s in range(args.warmup + args.steps):
+        r = cpu_reference_rate(budget_s=max(3.0, 100.0 / max(1, args.warmup + args.steps)))
+        if s >= args.warmup:
+            rates.append(r[0])
+        last = r
+    rate = float(np.mean(rates))
+    _, cores, kind, sample, wall = last
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "D: synthetic chain 2000 beads x 100 structures, dense contact list M=1997001, "
+                                   "posterior gradient (likelihood+nonbonded+backbone)"},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# own arm
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from ensemble_hic_b200 import engine
+    from ensemble_hic_b200.engine import Model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    R = REPLICAS_PER_GPU
+    n_total = R * world
+
+    pb = problem(rank, R)
+    N, S = pb["N"], pb["S"]
+    M = len(pb["i"])
+    # counts ~ Poisson(fwm(x*)) drawn from the (parity-tested) forward kernel at replica 0's x*
+    data0 = np.ascontiguousarray(np.stack([pb["i"], pb["j"], np.zeros(M, dtype=np.int64)], 1).astype(np.int64))
+    m0 = Model(S, pb["radii"], data0, pb["cds"], alpha=ALPHA, k_nb=K_NB, k_bb=K_BB, max_replicas=1, device=local)
+    md = m0.mock_data(pb["X"][0], 3.0)[0]
+    m0.close()
+    counts = np.random.default_rng(12345).poisson(md)        # same contact counts on every rank
+    data = np.ascontiguousarray(np.stack([pb["i"], pb["j"], counts], 1).astype(np.int64))
+    model = Model(S, pb["radii"], data, pb["cds"], alpha=ALPHA, k_nb=K_NB, k_bb=K_BB, max_replicas=R, device=local)
+    lad = ladder(n_total)[rank * R:(rank + 1) * R]
+
+    x = torch.tensor(pb["X"], dtype=torch.float64, device=dev)
+    norm = torch.full((R,), max(float(counts.max()) / S, 1.0), dtype=torch.float64, device=dev)
+    lam = torch.tensor(lad, dtype=torch.float64, device=dev)
+    bet = torch.tensor(lad, dtype=torch.float64, device=dev)
+    g = torch.empty_like(x)
+
+    def step():
+        model.evaluate_device(R, x, norm, lam, bet, grad=g)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = engine.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = engine.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    value = n_total * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public host API: pinned host buffers, H2D + D2H inside ------
+    xh = torch.empty(x.shape, dtype=torch.float64).pin_memory()
+    xh.copy_(x.cpu())
+    xh_np = xh.numpy()
+    normh, lamh, beth = norm.cpu().numpy(), lam.cpu().numpy(), bet.cpu().numpy()
+    gh = torch.empty((R, S * N * 3), dtype=torch.float64).pin_memory()
+    L = model._L
+    from ensemble_hic_b200 import _lib
+
+    def step_e2e():
+        _lib.check(L.ehic_evaluate_host(model._h, R, 15, xh_np.ctypes.data, normh.ctypes.data, lamh.ctypes.data,
+                                        beth.ctypes.data, gh.data_ptr(), None, None))
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(3, min(args.steps, 10))
+    for _ in range(n_e2e):
+        step_e2e()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = n_total * n_e2e / float(dt.item())
+    bytes_x = R * S * N * 3 * 8
+
+    # ---- per-kernel durations (CUDA events on the launching stream, same call sequence) ------
+    kern = None
+    if rank == 0:
+        kern = model.kernel_times(lambda: step(), repeats=max(3, min(args.steps, 10)))
+
+    if rank == 0:
+        peaks, peaks_kind = measured_peaks()
+        fp64_tf, _ = engine.fma_peak(True, 10, local)
+        fp32_tf, _ = engine.fma_peak(False, 10, local)
+        # dominant kernel: gather (likelihood gradient); algorithmic flop = 23 per (structure, data point)
+        gather_ms = kern.get("gather", None) if kern else None
+        flop_gather = FLOP_BWD_PER_PAIR * S * M * R
+        ach = flop_gather / (gather_ms * 1e-3) / 1e12 if gather_ms else None
+        flop_step = ((FLOP_FWD_PER_PAIR + FLOP_BWD_PER_PAIR) * S * M + FLOP_NB_PER_TEST * S * N * (N - 1) / 2) * R
+        bytes_step = (24.0 * S * N * 2 + 24.0 * M + 16.0 * M) * R
+        prof = {}
+        pj = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(pj):
+            with open(pj) as f:
+                prof = json.load(f)
+        roofline = {"bound": "fp64", "kernel": "gather_kernel", "achieved": ach, "peak": fp64_tf, "unit": "TFLOP/s",
+                    "frac": (ach / fp64_tf) if ach else None, "traffic": prof.get("gather_dram_bytes_per_launch"),
+                    "peak_source": "measured here: DFMA issue-rate micro-benchmark (ehic_fma_peak); FP64/FP32 "
+                                   "non-tensor peaks are not in MEASURED_PEAKS.json (SURVEY 8d)",
+                    "algorithmic_flop_per_launch": flop_gather, "kernel_ms": kern,
+                    "step": {"achieved": flop_step / (ms / args.steps * 1e-3) / 1e12, "peak": fp64_tf,
+                             "frac": flop_step / (ms / args.steps * 1e-3) / 1e12 / fp64_tf,
+                             "algorithmic_flop_per_step": flop_step},
+                    "fp32_peak_tflops": fp32_tf}
+        hbm_ach = bytes_step / (ms / args.steps * 1e-3) / 1e9
+        roofline_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": hbm_ach / peaks["hbm_gbs"], "peak_source": peaks_kind + " (MEASURED_PEAKS.json)",
+                        "note": "compulsory bytes of a whole step / step time; the path is FP64-pipe bound, not HBM bound",
+                        "traffic": prof.get("step_dram_bytes")}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, cores, kind, sample, _ = cpu_reference_rate(budget_s=15.0)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "D: synthetic chain 2000 beads x 100 structures, dense contact list M=%d, "
+                                       "%d replicas per GPU (%d total), posterior gradient "
+                                       "(likelihood+nonbonded+backbone)" % (M, R, n_total),
+                           "replicas_per_gpu": R, "n_beads": N, "n_structures": S, "n_data": M,
+                           "l2": "working set per step (contact rows 96 MB + weights 32 MB/replica + coordinates) "
+                                 "exceeds the 126 MB L2; no explicit flush"},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_x + 3 * R * 8,
+                        "d2h_bytes_per_step": bytes_x,
+                        "api": "ehic_evaluate_host (C ABI) with pinned host buffers, batched over the GPU's replicas"},
+                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -23,6 +23,13 @@ static std::atomic<long long> g_launches{0};
 
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
+struct ehic_model;
+struct KernelTimer {            // RAII: records a start event now and a stop event at scope exit
+    ehic_model *m; cudaStream_t st; int idx;
+    KernelTimer(ehic_model *m_, int cls, cudaStream_t st_);
+    ~KernelTimer();
+};
+
 #define CU(call)                                                                           \
     do {                                                                                   \
         cudaError_t e_ = (call);                                                           \
@@ -33,6 +40,8 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
 
+enum { KC_PACK = 0, KC_FORWARD, KC_PRIOR, KC_GATHER, KC_FINALIZE, KC_OTHER, KC_COUNT };
+
 struct ehic_model {
     int device = 0;
     int flags = 0;
@@ -41,18 +50,35 @@ struct ehic_model {
     ContactLayout layout;           // host copy (sizes, perm)
     std::vector<void *> owned;      // device allocations
     // workspace
-    double *xs[2] = {nullptr, nullptr};
+    double *xs[2] = {nullptr, nullptr};   // SoA working copies (forward + prior kernels)
+    double *xt[2] = {nullptr, nullptr};   // tile-AoS working copies (gather kernel)
     double *wbuf = nullptr, *gprior = nullptr;
     double *partA = nullptr, *partP = nullptr, *partK = nullptr;
     double *energies = nullptr, *kinetic = nullptr;
     int nA = 0;                     // forward blocks per replica
     int nPx = 0;                    // prior blocks per structure
-    int kt = 1, nkt = 1, nktg = 1;  // structures per warp, tiles per replica, tile groups (4 warps) per slice
+    int kt = 1, nkt = 1, nktg = 1;  // structures per warp, tiles per replica, tile groups (gw warps) per slice
+    int gw = 4;                     // warps per gather CTA
     double r_max = 0.0;
+    // optional per-kernel timing (ehic_profile): events bracket every launch on its stream
+    bool profiling = false;
+    struct Timed { int cls; cudaEvent_t a, b; };
+    std::vector<Timed> timed;
     // staging for the host entry points
     double *st_x = nullptr, *st_g = nullptr, *st_md = nullptr, *st_small = nullptr;
     cudaStream_t st_stream = nullptr;
 };
+
+KernelTimer::KernelTimer(ehic_model *m_, int cls, cudaStream_t st_) : m(m_), st(st_), idx(-1)
+{
+    if (!m->profiling) return;
+    ehic_model::Timed t; t.cls = cls;
+    if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return;
+    cudaEventRecord(t.a, st);
+    m->timed.push_back(t);
+    idx = (int)m->timed.size() - 1;
+}
+KernelTimer::~KernelTimer() { if (idx >= 0) cudaEventRecord(m->timed[idx].b, st); }
 
 template <typename T>
 static int upload(ehic_model *m, const std::vector<T> &v, const T **out)
@@ -106,6 +132,21 @@ static int check_device(int device)
     if (major != 10)
         return fail(EHIC_ERR_NODEVICE, "device is not compute capability 10.x (kernels are built for sm_100a only)");
     return EHIC_OK;
+}
+
+// warps per gather CTA: all warps of a CTA share one slice's row stream, so more warps mean
+// less L2 traffic; pick the count that wastes the fewest warp slots on the last tile group.
+static int pick_gw(int nkt)
+{
+    const char *env = getenv("EHIC_GW");
+    if (env) { int v = atoi(env); if (v >= 1 && v <= EHIC_GATHER_MAX_WARPS) return v; }
+    if (nkt <= 4) return nkt < 1 ? 1 : nkt;
+    int best = 4; double best_eff = 0.0;
+    for (int w = 4; w <= 8; w++) {
+        double eff = (double)nkt / (double)(((nkt + w - 1) / w) * w);
+        if (eff >= best_eff) { best_eff = eff; best = w; }
+    }
+    return best;
 }
 
 static int pick_kt(int S)
@@ -187,7 +228,8 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
 
     m->kt = pick_kt(S);
     m->nkt = (S + m->kt - 1) / m->kt;
-    m->nktg = (m->nkt + EHIC_GATHER_WARPS - 1) / EHIC_GATHER_WARPS;
+    m->gw = pick_gw(m->nkt);
+    m->nktg = (m->nkt + m->gw - 1) / m->gw;
     m->nA = (int)((L.M + 255) / 256);
     m->nPx = (N + EHIC_PRIOR_THREADS - 1) / EHIC_PRIOR_THREADS;
     const size_t Rm = (size_t)desc->max_replicas;
@@ -195,11 +237,15 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
 #define DA(ptr, n)                                                   \
     do { rc = dalloc(m, &(ptr), (n)); if (rc) { ehic_model_destroy(m); return rc; } } while (0)
     DA(m->xs[0], xs_n); DA(m->xs[1], xs_n);
+    const size_t xt_n = Rm * m->nkt * (size_t)dm.Np * m->kt * 3;
+    DA(m->xt[0], xt_n); DA(m->xt[1], xt_n);
+    for (int q = 0; q < 2; q++)     // records of padding structures (k >= S) stay zero forever
+        if (cudaMemset(m->xt[q], 0, xt_n * sizeof(double)) != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed"); }
     DA(m->wbuf, Rm * (size_t)dm.wstride);
     DA(m->gprior, Rm * S * (size_t)N * 3);
     DA(m->partA, Rm * (size_t)std::max(m->nA, 1));
     DA(m->partP, Rm * (size_t)S * m->nPx * 3);
-    DA(m->partK, Rm * (size_t)L.n_slices * m->nktg * EHIC_GATHER_WARPS);
+    DA(m->partK, Rm * (size_t)L.n_slices * m->nktg * m->gw);
     DA(m->energies, Rm * 4); DA(m->kinetic, Rm);
 #undef DA
     // weights of padding slots are never read (ent_j < 0), but keep the buffer defined
@@ -262,7 +308,7 @@ int ehic_model_info(const ehic_model_t *m, int64_t out[8])
 {
     if (!m || !out) return fail(EHIC_ERR_INVALID, "null argument");
     out[0] = m->dm.N; out[1] = m->dm.S; out[2] = m->dm.M; out[3] = m->max_replicas;
-    out[4] = m->flags; out[5] = m->dm.tot; out[6] = m->device; out[7] = m->kt;
+    out[4] = m->flags; out[5] = m->dm.tot; out[6] = m->device; out[7] = m->kt * 100 + m->gw;
     return EHIC_OK;
 }
 
@@ -278,10 +324,11 @@ static int check_call(ehic_model *m, int R)
     return EHIC_OK;
 }
 
-static int launch_pack(ehic_model *m, int R, const double *d_x, double *xs, cudaStream_t st)
+static int launch_pack(ehic_model *m, int R, const double *d_x, double *xs, double *xt, cudaStream_t st)
 {
     long long rows = (long long)R * m->dm.S, total = rows * m->dm.Np;
-    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_x, xs, m->dm.N, m->dm.Np, rows);
+    KernelTimer kt_(m, KC_PACK, st);
+    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_x, xs, xt, m->dm.N, m->dm.Np, m->dm.S, m->kt, m->nkt, rows);
     LAUNCHED();
     CU(cudaGetLastError());
     return EHIC_OK;
@@ -295,6 +342,7 @@ static int launch_forward(ehic_model *m, int R, const double *xs, const double *
         return EHIC_OK;
     }
     dim3 grid((unsigned)m->nA, (unsigned)R);
+    KernelTimer kt_(m, KC_FORWARD, st);
     if (m->flags & EHIC_FLAG_EXACT)
         forward_kernel<true><<<grid, 256, 0, st>>>(m->dm, xs, d_norm, d_md, want_w ? m->wbuf : nullptr, m->partA, want_logl);
     else
@@ -309,6 +357,7 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
 {
     dim3 grid((unsigned)m->nPx, (unsigned)m->dm.S, (unsigned)R);
     double *gp = want_grad ? m->gprior : nullptr, *pp = want_energy ? m->partP : nullptr;
+    KernelTimer kt_(m, KC_PRIOR, st);
     if (m->flags & EHIC_FLAG_EXACT)
         prior_kernel<true><<<grid, EHIC_PRIOR_THREADS, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max);
     else
@@ -322,7 +371,7 @@ template <bool EXACT>
 static void launch_gather_t(ehic_model *m, const GatherArgs &ga, int R, cudaStream_t st)
 {
     unsigned blocks = (unsigned)((long long)R * m->dm.n_slices * m->nktg);
-    const int threads = EHIC_GATHER_WARPS * 32;
+    const int threads = m->gw * 32;
     switch (m->kt) {
     case 4: gather_kernel<EXACT, 4><<<blocks, threads, 0, st>>>(m->dm, ga, m->nkt, m->nktg); break;
     case 2: gather_kernel<EXACT, 2><<<blocks, threads, 0, st>>>(m->dm, ga, m->nkt, m->nktg); break;
@@ -333,6 +382,7 @@ static void launch_gather_t(ehic_model *m, const GatherArgs &ga, int R, cudaStre
 
 static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_t st)
 {
+    KernelTimer kt_(m, KC_GATHER, st);
     if (m->flags & EHIC_FLAG_EXACT) launch_gather_t<true>(m, ga, R, st);
     else launch_gather_t<false>(m, ga, R, st);
     CU(cudaGetLastError());
@@ -342,9 +392,10 @@ static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_
 static int launch_finalize(ehic_model *m, int R, bool haveA, bool haveP, bool haveK,
                            double *d_energies, double *d_kin, cudaStream_t st)
 {
+    KernelTimer kt_(m, KC_FINALIZE, st);
     finalize_kernel<<<R, 256, 0, st>>>(m->dm, haveA ? m->partA : nullptr, m->nA,
                                        haveP ? m->partP : nullptr, (long long)m->dm.S * m->nPx,
-                                       haveK ? m->partK : nullptr, (long long)m->dm.n_slices * m->nktg * EHIC_GATHER_WARPS,
+                                       haveK ? m->partK : nullptr, (long long)m->dm.n_slices * m->nktg * m->gw,
                                        d_energies, d_kin);
     LAUNCHED();
     CU(cudaGetLastError());
@@ -361,7 +412,7 @@ int ehic_mock_data(ehic_model_t *m, int R, const double *d_x, const double *d_no
     if (rc) return rc;
     if (!d_x || !d_norm || !d_md) return fail(EHIC_ERR_INVALID, "null buffer");
     cudaStream_t st = (cudaStream_t)stream;
-    rc = launch_pack(m, R, d_x, m->xs[0], st);
+    rc = launch_pack(m, R, d_x, m->xs[0], nullptr, st);
     if (rc) return rc;
     return launch_forward(m, R, m->xs[0], d_norm, d_md, false, false, st);
 }
@@ -379,7 +430,7 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     const int prior_terms = terms & ~EHIC_TERM_LIKELIHOOD;
     if ((lik || d_md) && !d_norm) return fail(EHIC_ERR_INVALID, "norm required for the likelihood term");
     cudaStream_t st = (cudaStream_t)stream;
-    rc = launch_pack(m, R, d_x, m->xs[0], st);
+    rc = launch_pack(m, R, d_x, m->xs[0], d_grad ? m->xt[0] : nullptr, st);
     if (rc) return rc;
     const bool need_forward = (lik && (d_grad || d_energies)) || d_md;
     if (need_forward) {
@@ -393,7 +444,7 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     }
     if (d_grad) {
         GatherArgs ga{};
-        ga.xs = m->xs[0]; ga.wbuf = m->wbuf; ga.lammda = d_lammda;
+        ga.xt = m->xt[0]; ga.wbuf = m->wbuf; ga.lammda = d_lammda;
         ga.gprior = need_prior ? m->gprior : nullptr;
         ga.grad = d_grad; ga.contact = lik ? 1 : 0;
         rc = launch_gather(m, ga, R, st);
@@ -417,7 +468,7 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
     cudaStream_t st = (cudaStream_t)stream;
     int prior_terms = EHIC_TERM_ALL & ~EHIC_TERM_LIKELIHOOD;
     if (!m->dm.sphere_active) prior_terms &= ~EHIC_TERM_SPHERE;
-    rc = launch_pack(m, R, d_x, m->xs[0], st);
+    rc = launch_pack(m, R, d_x, m->xs[0], m->xt[0], st);
     if (rc) return rc;
     int cur = 0;
     for (int s = 0; s <= n_steps; s++) {
@@ -428,10 +479,11 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
         rc = launch_prior(m, R, prior_terms, m->xs[cur], d_beta, true, ends, st);
         if (rc) return rc;
         GatherArgs ga{};
-        ga.xs = m->xs[cur]; ga.wbuf = m->wbuf; ga.lammda = d_lammda; ga.gprior = m->gprior;
+        ga.xt = m->xt[cur]; ga.wbuf = m->wbuf; ga.lammda = d_lammda; ga.gprior = m->gprior;
         ga.grad = nullptr; ga.partK = ends ? m->partK : nullptr; ga.contact = 1;
         ga.p = d_p; ga.eps = d_eps; ga.kick = ends ? 0.5 : 1.0;
         ga.xs_next = last ? nullptr : m->xs[cur ^ 1];
+        ga.xt_next = last ? nullptr : m->xt[cur ^ 1];
         ga.kinetic_mode = first ? 1 : (last ? 2 : 0);
         rc = launch_gather(m, ga, R, st);
         if (rc) return rc;
@@ -547,6 +599,30 @@ int ehic_evaluate_host(ehic_model_t *m, int R, int terms, const double *h_x, con
     if (h_energies) CU(cudaMemcpyAsync(h_energies, d_E, sizeof(double) * 4 * R, cudaMemcpyDeviceToHost, st));
     if (h_md && m->dm.M > 0) CU(cudaMemcpyAsync(h_md, m->st_md, sizeof(double) * (size_t)R * m->dm.M, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return EHIC_OK;
+}
+
+// ---- per-kernel timing ------------------------------------------------------------------------
+
+int ehic_profile(ehic_model_t *m, int enable)
+{
+    if (!m) return fail(EHIC_ERR_INVALID, "null model");
+    m->profiling = enable != 0;
+    return EHIC_OK;
+}
+
+int ehic_profile_read(ehic_model_t *m, double ms_out[8], int64_t count_out[8])
+{
+    if (!m || !ms_out || !count_out) return fail(EHIC_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(m->device));
+    CU(cudaDeviceSynchronize());
+    for (int q = 0; q < 8; q++) { ms_out[q] = 0.0; count_out[q] = 0; }
+    for (auto &t : m->timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { ms_out[t.cls] += ms; count_out[t.cls]++; }
+        cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+    }
+    m->timed.clear();
     return EHIC_OK;
 }
 

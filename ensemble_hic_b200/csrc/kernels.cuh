@@ -61,9 +61,13 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // ---------------------------------------------------------------------------------------
-// x[R][S][N][3] -> xs[R][S][3][Np]
-__global__ void pack_kernel(const double *__restrict__ x, double *__restrict__ xs,
-                            int N, int Np, long long rows /* R*S */)
+// x[R][S][N][3] -> xs[R][S][3][Np]  and  xt[R][nkt][Np][KT][3]
+//
+// xt ("tile-AoS") is the gather kernel's copy: one record holds bead o of the KT structures of
+// one structure tile (KT*24 B, contiguous), so a partner costs one address computation and
+// KT*3/2 LDG.128 instead of KT*3 separately addressed LDG.64.
+__global__ void pack_kernel(const double *__restrict__ x, double *__restrict__ xs, double *__restrict__ xt,
+                            int N, int Np, int S, int KT, int nkt, long long rows /* R*S */)
 {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = rows * Np;
@@ -77,6 +81,12 @@ __global__ void pack_kernel(const double *__restrict__ x, double *__restrict__ x
     }
     double *q = xs + row * 3 * (long long)Np + i;
     q[0] = a; q[Np] = b; q[2 * (long long)Np] = c;
+    if (xt && i < N) {
+        long long r = row / S;
+        int k = (int)(row - r * S);
+        double *u = xt + (((r * nkt + k / KT) * Np + i) * KT + (k % KT)) * 3;
+        u[0] = a; u[1] = b; u[2] = c;
+    }
 }
 
 // xs[R][S][3][Np] -> x[R][S][N][3]
@@ -180,6 +190,23 @@ forward_kernel(DevModel dm, const double *__restrict__ xs, const double *__restr
             for (int q = 0; q < 8; q++) t += sh[q];
             partA[(long long)r * gridDim.x + blockIdx.x] = t;
         }
+    }
+}
+
+// One tile-AoS record (KT*3 doubles, 16-byte aligned when KT is even) -> registers.
+template <int KT>
+__device__ __forceinline__ void load_record(const double *__restrict__ p, double (&v)[KT * 3])
+{
+    if constexpr (KT % 2 == 0) {
+        const double2 *q = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+        for (int u = 0; u < KT * 3 / 2; u++) {
+            double2 w = q[u];
+            v[2 * u] = w.x; v[2 * u + 1] = w.y;
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < KT * 3; u++) v[u] = p[u];
     }
 }
 
@@ -368,12 +395,12 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
 // Epilogue: grad = lammda * g + gprior; optional leapfrog kick + drift (HMC trajectories keep
 // x and p on the device) and kinetic-energy partials.
 // No atomics anywhere: every output element has exactly one writer and a fixed summation order.
-#define EHIC_GATHER_WARPS 4
+#define EHIC_GATHER_MAX_WARPS 16
 #define EHIC_CHUNK 16      // row entries per pipeline stage
 #define EHIC_STAGES 3
 
 struct GatherArgs {
-    const double *xs;       // [R][S][3][Np] positions the gradient is evaluated at
+    const double *xt;       // [R][nkt][Np][KT][3] positions the gradient is evaluated at (tile-AoS)
     const double *wbuf;     // [R][tot+pad] per-slot Poisson weights (from forward_kernel)
     const double *lammda;   // [R] or NULL
     const double *gprior;   // [R][S][N][3] or NULL
@@ -384,12 +411,13 @@ struct GatherArgs {
     double *p;              // [R][S][N][3] momenta, updated in place:  p -= kick * eps * g
     const double *eps;      // [R]
     double kick;            // 0.5 or 1.0
-    double *xs_next;        // [R][S][3][Np]: xs + eps * p (after the kick), or NULL (no drift)
+    double *xs_next;        // [R][S][3][Np]: x + eps * p (after the kick), or NULL (no drift)
+    double *xt_next;        // the same in tile-AoS layout
     int kinetic_mode;       // partK = sum p^2 before the kick (1) / after the kick (2) / none (0)
 };
 
 template <bool EXACT, int KT>
-__global__ void __launch_bounds__(EHIC_GATHER_WARPS * 32)
+__global__ void __launch_bounds__(EHIC_GATHER_MAX_WARPS * 32)
 gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
 {
     __shared__ __align__(16) int s_o[EHIC_STAGES][EHIC_CHUNK * 32];
@@ -401,7 +429,8 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
     const int tmp = blockIdx.x / nktg;
     const int sl = tmp % dm.n_slices;
     const int r = tmp / dm.n_slices;
-    const int kt = ktg * EHIC_GATHER_WARPS + warp;
+    const int n_warps = blockDim.x >> 5;
+    const int kt = ktg * n_warps + warp;
     const bool kt_ok = kt < nkt;
     const int b = sl * 32 + lane;
     const bool bead_ok = b < dm.N;
@@ -410,17 +439,19 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
     const long long plane = 3LL * Np;
     const int k0 = (kt_ok ? kt : 0) * KT;
 
-    const double *xk[KT];
+    // records of this structure tile: bead o -> KT*3 contiguous doubles
+    const double *xrec = ga.xt + ((long long)r * nkt + (kt_ok ? kt : 0)) * Np * (KT * 3);
     bool k_ok[KT];
     double xb[KT][3], acc[KT][3];
+    {
+        double v[KT * 3];
+        load_record<KT>(xrec + (long long)bb * (KT * 3), v);
 #pragma unroll
-    for (int t = 0; t < KT; t++) {
-        int k = k0 + t;
-        k_ok[t] = kt_ok && k < dm.S;
-        if (k >= dm.S) k = dm.S - 1;
-        xk[t] = ga.xs + ((long long)r * dm.S + k) * plane;
-        xb[t][0] = xk[t][bb]; xb[t][1] = xk[t][Np + bb]; xb[t][2] = xk[t][2 * Np + bb];
-        acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
+        for (int t = 0; t < KT; t++) {
+            k_ok[t] = kt_ok && (k0 + t) < dm.S;
+            xb[t][0] = v[3 * t]; xb[t][1] = v[3 * t + 1]; xb[t][2] = v[3 * t + 2];
+            acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
+        }
     }
 
     if (ga.contact && dm.M > 0) {
@@ -432,16 +463,17 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
         const double *gw = ga.wbuf + (long long)r * dm.wstride + off;
         const double alpha = dm.alpha;
         const double aa = __dmul_rn(alpha, alpha);
-        const int tid = threadIdx.x;
+        // one chunk = 16 entries x 32 lanes: 2 KB of partner indices + 4 KB + 4 KB of doubles,
+        // moved as 640 16-byte cp.async copies spread over the CTA's threads
         auto issue = [&](int c) {
             if (c < nchunks) {
                 const int st = c % EHIC_STAGES;
                 const long long base = (long long)c * EHIC_CHUNK * 32;
-                __pipeline_memcpy_async(&s_o[st][tid * 4], gj + base + tid * 4, 16);
-                __pipeline_memcpy_async(&s_dc[st][tid * 2], gdc + base + tid * 2, 16);
-                __pipeline_memcpy_async(&s_dc[st][256 + tid * 2], gdc + base + 256 + tid * 2, 16);
-                __pipeline_memcpy_async(&s_w[st][tid * 2], gw + base + tid * 2, 16);
-                __pipeline_memcpy_async(&s_w[st][256 + tid * 2], gw + base + 256 + tid * 2, 16);
+                for (int q = threadIdx.x; q < 640; q += blockDim.x) {
+                    if (q < 128) __pipeline_memcpy_async(&s_o[st][q * 4], gj + base + q * 4, 16);
+                    else if (q < 384) __pipeline_memcpy_async(&s_dc[st][(q - 128) * 2], gdc + base + (q - 128) * 2, 16);
+                    else __pipeline_memcpy_async(&s_w[st][(q - 384) * 2], gw + base + (q - 384) * 2, 16);
+                }
             }
             __pipeline_commit();
         };
@@ -458,9 +490,11 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
                 const int o = s_o[st][e * 32 + lane];
                 const double dc = s_dc[st][e * 32 + lane];
                 const double w = s_w[st][e * 32 + lane];
+                double v[KT * 3];
+                load_record<KT>(xrec + (long long)o * (KT * 3), v);
 #pragma unroll
                 for (int t = 0; t < KT; t++) {
-                    const double ox = xk[t][o], oy = xk[t][Np + o], oz = xk[t][2 * Np + o];
+                    const double ox = v[3 * t], oy = v[3 * t + 1], oz = v[3 * t + 2];
                     if (EXACT) {
                         // likelihoods_c.pyx:64-73 with d, sqrtdenoms recomputed as in pxd:33-37
                         double d0 = __dsub_rn(xb[t][0], ox), d1 = __dsub_rn(xb[t][1], oy), d2 = __dsub_rn(xb[t][2], oz);
@@ -512,16 +546,17 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
             ga.p[at] = p0; ga.p[at + 1] = p1; ga.p[at + 2] = p2;
             if (ga.kinetic_mode == 2) kin += p0 * p0 + p1 * p1 + p2 * p2;
             if (ga.xs_next) {
+                const double n0 = fma(eps, p0, xb[t][0]), n1 = fma(eps, p1, xb[t][1]), n2 = fma(eps, p2, xb[t][2]);
                 double *xn = ga.xs_next + ((long long)r * dm.S + k) * plane;
-                xn[b] = fma(eps, p0, xb[t][0]);
-                xn[Np + b] = fma(eps, p1, xb[t][1]);
-                xn[2 * Np + b] = fma(eps, p2, xb[t][2]);
+                xn[b] = n0; xn[Np + b] = n1; xn[2 * Np + b] = n2;
+                double *un = ga.xt_next + ((((long long)r * nkt + kt) * Np + b) * KT + t) * 3;
+                un[0] = n0; un[1] = n1; un[2] = n2;
             }
         }
     }
     if (ga.partK) {
         kin = warp_sum(kin);
-        if (lane == 0) ga.partK[(long long)blockIdx.x * EHIC_GATHER_WARPS + warp] = kin;
+        if (lane == 0) ga.partK[(long long)blockIdx.x * n_warps + warp] = kin;
     }
 }
 

@@ -106,6 +106,23 @@ class Model(object):
         return dict(N=out[0], S=out[1], M=out[2], max_replicas=out[3], flags=out[4], slots=out[5],
                     device=out[6], kt=out[7])
 
+    # ---- per-kernel timing ------------------------------------------------------------------
+    KERNEL_CLASSES = ("pack", "forward", "prior", "gather", "finalize", "other")
+
+    def kernel_times(self, fn, repeats=5):
+        """Average device milliseconds per call of ``fn`` spent in each kernel class (CUDA events
+        recorded by the library on the launching stream)."""
+        ms = (C.c_double * 8)(); cnt = (C.c_int64 * 8)()
+        _lib.check(self._L.ehic_profile(self._h, 1))
+        try:
+            _lib.check(self._L.ehic_profile_read(self._h, ms, cnt))     # drop anything pending
+            for _ in range(repeats):
+                fn()
+            _lib.check(self._L.ehic_profile_read(self._h, ms, cnt))
+        finally:
+            self._L.ehic_profile(self._h, 0)
+        return {n: ms[q] / repeats for q, n in enumerate(self.KERNEL_CLASSES) if cnt[q]}
+
     # ---- host API -------------------------------------------------------------------------
     def _prep(self, x, norm, lammda, beta):
         x = _f64(x)

@@ -169,6 +169,13 @@ int ehic_evaluate_host(ehic_model_t *m, int R, int terms, const double *h_x, con
 int ehic_layout_debug(int32_t n_beads, int64_t n_data, const int64_t *data_points, int exact_order,
                       int64_t *h_sorted, int64_t *n_slots, int32_t *h_row_len /* [N] */);
 
+/* ---- per-kernel timing: with profiling enabled every kernel launch of this model is bracketed
+ * by CUDA events on the stream it is launched on; ehic_profile_read synchronises the device and
+ * returns (and resets) the summed milliseconds and launch counts per kernel class:
+ * 0 pack, 1 forward, 2 prior, 3 gather, 4 finalize, 5 other. */
+int ehic_profile(ehic_model_t *m, int enable);
+int ehic_profile_read(ehic_model_t *m, double ms_out[8], int64_t count_out[8]);
+
 /* ---- measurement helpers ---------------------------------------------------------------
  * FP64 / FP32 FMA issue-rate micro-benchmark (the non-tensor pipe peaks are not
  * in MEASURED_PEAKS.json).  Returns achieved TFLOP/s (2 flop per FMA) over `iters` launches. */
