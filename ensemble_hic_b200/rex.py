@@ -1,0 +1,334 @@
+"""Batched multi-GPU replica exchange: one process per GPU, the replica ladder partitioned
+contiguously over the ranks, every local replica advanced by ONE batched device call per HMC
+trajectory, exchanges decided from ENERGIES ONLY.
+
+Reference being replaced: one MPI process per replica + a master
+(run_simulation.py:17-21, 49-108) that ships whole states between partner processes and
+re-evaluates the full posterior on the foreign state (replica.py:12-14).  Here tempering is
+linear in two untempered terms,
+
+    E_t(state) = lammda_t * U_L(state) + beta_t * U_nb(state) + U_rest(state),
+
+so the work of exchanging temperatures t and t+1 held by slots a and b is
+
+    w = (lammda_t - lammda_t+1) * (U_L(b) - U_L(a)) + (beta_t - beta_t+1) * (U_nb(b) - U_nb(a))
+
+(U_rest cancels).  Each exchange round all-gathers (U_L, U_nb) of every slot -- 16 bytes per
+replica over NCCL -- and every rank takes the same accept/reject decisions from a shared seeded
+uniform stream, then permutes the temperature -> slot map.  Coordinates never move; what
+follows the *temperature* is (lammda, beta, HMC timestep and its acceptance statistics, and the
+sample file), because the reference's outputs are per temperature
+(analysis_functions.py:66-69, setup_continue.py:53-54).
+
+The rexfw package (ExchangeMaster, Replica, Slave, statistics writers) is absent from the
+reference tree; swap schedule (alternating neighbour pairs every ``swap_interval``-th step),
+acceptance rule min(1, exp(-w)) and the file layout are restated from the reference's call
+sites and from its continuation / analysis scripts: "parity unpinned" (SURVEY.md 8c).
+"""
+import os
+import pickle
+import shutil
+
+import numpy as np
+
+from ._binf import BinfState
+
+
+def partition(n_replicas, world_size):
+    """contiguous blocks of the ladder: rank r holds slots [bounds[r], bounds[r+1])"""
+    base, extra = divmod(n_replicas, world_size)
+    sizes = [base + (1 if r < extra else 0) for r in range(world_size)]
+    return np.concatenate(([0], np.cumsum(sizes))).astype(int)
+
+
+def swap_pairs(n_replicas, round_index):
+    """neighbouring temperature pairs of one exchange round: (0,1),(2,3).. on even rounds,
+    (1,2),(3,4).. on odd rounds (rexfw create_default_RE_params)."""
+    start = round_index % 2
+    return [(t, t + 1) for t in range(start, n_replicas - 1, 2)]
+
+
+def decide_swaps(pairs, slot_of_temp, U, lammda, beta, uniforms):
+    """Accept/reject every pair from the gathered energies.  U[slot] = (U_L, U_nb).
+    Returns (list of accepted flags, list of works)."""
+    acc, works = [], []
+    for (t0, t1), u in zip(pairs, uniforms):
+        a, b = slot_of_temp[t0], slot_of_temp[t1]
+        w = (lammda[t0] - lammda[t1]) * (U[b, 0] - U[a, 0]) + (beta[t0] - beta[t1]) * (U[b, 1] - U[a, 1])
+        ok = bool(np.isfinite(w) and np.log(max(u, 1e-300)) < -w)
+        acc.append(ok); works.append(float(w))
+    return acc, works
+
+
+class EngineBackend(object):
+    """Device side of the driver: the resident CUDA model (product path)."""
+
+    def __init__(self, model, device=None):
+        import torch
+        self.torch = torch
+        self.m = model
+        self.device = torch.device("cuda", model.device) if device is None else device
+        self.n_dof = model.S * model.N * 3
+
+    def tensor(self, a):
+        return self.torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)
+
+    def energies(self, x, norm):
+        R = x.shape[0]
+        E = self.torch.empty(R, 4, dtype=self.torch.float64, device=self.device)
+        with self.torch.cuda.device(self.device):
+            self.m.evaluate_device(R, x, norm, None, None, grad=None, energies=E)
+        return E
+
+    def trajectory(self, x, p, norm, lam, beta, eps, n_steps):
+        R = x.shape[0]
+        H = self.torch.empty(R, 4, dtype=self.torch.float64, device=self.device)
+        with self.torch.cuda.device(self.device):
+            self.m.hmc_trajectory_device(R, n_steps, x, p, norm, lam, beta, eps, H)
+        return H
+
+    def mock_sums(self, x):
+        """sum_m fwm(x, norm=1)_m per replica (npsamplers.py:110-116)"""
+        R = x.shape[0]
+        one = self.torch.ones(R, dtype=self.torch.float64, device=self.device)
+        md = self.torch.empty(R, self.m.M, dtype=self.torch.float64, device=self.device)
+        with self.torch.cuda.device(self.device):
+            self.m.mock_data_device(R, x, one, md)
+        return md.sum(dim=1)
+
+    def select(self, mask, src, dst):
+        from .engine import select_device
+        with self.torch.cuda.device(self.device):
+            select_device(src.shape[0], src.shape[1], mask, src, dst)
+
+
+class ReplicaExchange(object):
+    """The whole simulation loop of run_simulation.py for the slots of this rank.
+
+    backend      EngineBackend (or a test double with the same five methods)
+    schedule     {'lammda': [T], 'beta': [T]} for the full ladder
+    x0, norm0    initial states of the LOCAL slots: [R_local, n_dof], [R_local]
+    hmc          dict(timestep, trajectory_length, adaption_limit)
+    norm_prior   (shape, rate) of the Gamma prior if norm is sampled, else None
+    counts_sum   sum of the contact counts (shape of the conditional Gamma)
+    """
+
+    def __init__(self, backend, schedule, x0, norm0, hmc, norm_prior=None, counts_sum=0.0,
+                 output_folder=None, seed=0, rank=0, world_size=1, dist=None, momenta="numpy"):
+        self.be = backend
+        self.lam_T = np.asarray(schedule["lammda"], dtype=np.float64)
+        self.bet_T = np.asarray(schedule["beta"], dtype=np.float64)
+        self.T = len(self.lam_T)
+        self.rank, self.world, self.dist = rank, world_size, dist
+        self.bounds = partition(self.T, world_size)
+        self.lo, self.hi = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.R = self.hi - self.lo
+        assert np.shape(x0)[0] == self.R, "x0 must hold the local slots"
+        self.x = backend.tensor(np.array(x0, dtype=np.float64))
+        self.norm = backend.tensor(np.array(np.broadcast_to(norm0, (self.R,)), dtype=np.float64))
+        self.L = int(hmc["trajectory_length"])
+        self.adaption_limit = int(hmc.get("adaption_limit", 0))
+        self.up, self.down = float(hmc.get("adaption_uprate", 1.05)), float(hmc.get("adaption_downrate", 0.95))
+        # per-TEMPERATURE quantities (identical on every rank)
+        self.timestep_T = np.full(self.T, float(hmc["timestep"]))
+        self.n_acc_T = np.zeros(self.T); self.n_hmc_T = np.zeros(self.T)
+        self.re_acc = np.zeros(max(self.T - 1, 1)); self.re_try = np.zeros(max(self.T - 1, 1))
+        self.temp_of_slot = np.arange(self.T)
+        self.slot_of_temp = np.arange(self.T)
+        self.norm_prior, self.counts_sum = norm_prior, float(counts_sum)
+        self.out = output_folder
+        self.momenta = momenta
+        self.rng_swap = np.random.RandomState(seed)                       # shared by all ranks
+        self.rng_slot = [np.random.RandomState(seed + 1 + s) for s in range(self.lo, self.hi)]
+        self.n_swap_rounds = 0
+        self.step = 0
+        self._buffer = {}          # temperature -> [(step, BinfState)]
+        self.works = []
+        self.last_accept = np.zeros(self.R, dtype=bool)
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def _local_temps(self):
+        return self.temp_of_slot[self.lo:self.hi]
+
+    def _allgather_rows(self, local, width):
+        """gather [R_local, width] rows of every rank into a [T, width] numpy array"""
+        torch = self.be.torch if hasattr(self.be, "torch") else None
+        if self.world == 1 or self.dist is None:
+            return local.detach().cpu().numpy() if hasattr(local, "detach") else np.asarray(local)
+        rmax = int(np.max(np.diff(self.bounds)))
+        pad = torch.zeros(rmax, width, dtype=local.dtype, device=local.device)
+        pad[:self.R] = local
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(out, pad)
+        rows = [out[r][:self.bounds[r + 1] - self.bounds[r]] for r in range(self.world)]
+        return torch.cat(rows).cpu().numpy()
+
+    # ---- one Gibbs sample for every local slot ------------------------------------------------------
+    def sample(self):
+        be, temps = self.be, self._local_temps()
+        lam, bet = be.tensor(self.lam_T[temps]), be.tensor(self.bet_T[temps])
+        eps = be.tensor(self.timestep_T[temps])
+        if self.momenta == "numpy":
+            p = be.tensor(np.stack([rs.normal(size=be.n_dof) for rs in self.rng_slot]))
+        else:
+            p = be.torch.randn(self.R, be.n_dof, dtype=be.torch.float64, device=self.x.device)
+        x_new = self.x.clone()
+        H = be.trajectory(x_new, p, self.norm, lam, bet, eps, self.L)
+        Hh = H.detach().cpu().numpy()
+        dH = (Hh[:, 2] + Hh[:, 3]) - (Hh[:, 0] + Hh[:, 1])
+        u = np.array([rs.random_sample() for rs in self.rng_slot])
+        acc = np.isfinite(dH) & (np.log(np.maximum(u, 1e-300)) < -dH)
+        mask = be.tensor(acc.astype(np.float64)).to(dtype=be.torch.int32)
+        be.select(mask, x_new, self.x)
+        self.last_accept = acc
+        # statistics / adaptation follow the temperature; share them with the other ranks
+        stat = np.zeros((self.R, 1)); stat[:, 0] = acc
+        all_acc = self._allgather_rows(be.tensor(stat), 1)[:, 0]
+        for s in range(self.T):
+            t = self.temp_of_slot[s]
+            self.n_hmc_T[t] += 1
+            self.n_acc_T[t] += all_acc[s]
+            if self.n_hmc_T[t] < self.adaption_limit:
+                self.timestep_T[t] *= self.up if all_acc[s] > 0.5 else self.down
+        # conjugate Gamma draw for the scaling factor (npsamplers.py:42-116)
+        if self.norm_prior is not None:
+            sums = be.mock_sums(self.x).detach().cpu().numpy()
+            new = np.empty(self.R)
+            for q in range(self.R):
+                lam_q = self.lam_T[temps[q]]
+                shape = lam_q * self.counts_sum + self.norm_prior[0]
+                rate = lam_q * sums[q] + self.norm_prior[1]
+                v = self.rng_slot[q].gamma(shape) / rate
+                new[q] = v if v != 0.0 else 1e-10
+            self.norm = be.tensor(new)
+        return acc
+
+    # ---- one exchange round ----------------------------------------------------------------------------
+    def exchange(self):
+        E = self.be.energies(self.x, self.norm)
+        U = self._allgather_rows(E[:, :2].contiguous(), 2)            # [T slots, (U_L, U_nb)]
+        pairs = swap_pairs(self.T, self.n_swap_rounds)
+        uniforms = self.rng_swap.random_sample(len(pairs))
+        acc, works = decide_swaps(pairs, self.slot_of_temp, U, self.lam_T, self.bet_T, uniforms)
+        for (t0, t1), ok in zip(pairs, acc):
+            self.re_try[t0] += 1
+            if ok:
+                self.re_acc[t0] += 1
+                a, b = self.slot_of_temp[t0], self.slot_of_temp[t1]
+                self.slot_of_temp[t0], self.slot_of_temp[t1] = b, a
+                self.temp_of_slot[a], self.temp_of_slot[b] = t1, t0
+        self.works.append((self.step, pairs, works, acc))
+        self.n_swap_rounds += 1
+        return acc
+
+    # ---- output -------------------------------------------------------------------------------------------
+    def _record(self):
+        xs = self.x.detach().cpu().numpy()
+        ns = self.norm.detach().cpu().numpy()
+        for q, t in enumerate(self._local_temps()):
+            v = {"structures": xs[q].copy()}
+            if self.norm_prior is not None:
+                v["norm"] = float(ns[q])
+            self._buffer.setdefault(int(t), []).append((self.step, BinfState(v)))
+
+    def _dump(self, first, last, dump_step):
+        """samples/samples_replica{t+1}_{first}-{last}.pickle: list of states, thinned by dump_step.
+        Records of temperatures whose home rank is another rank travel there now (I/O, not hot path)."""
+        if self.out is None:
+            self._buffer = {}
+            return
+        home = lambda t: int(np.searchsorted(self.bounds, t, side="right") - 1)
+        mine, away = {}, {}
+        for t, recs in self._buffer.items():
+            (mine if home(t) == self.rank else away).setdefault(t, []).extend(recs)
+        if self.world > 1 and self.dist is not None:
+            gathered = [None] * self.world
+            self.dist.all_gather_object(gathered, away)
+            for other in gathered:
+                for t, recs in other.items():
+                    if home(t) == self.rank:
+                        mine.setdefault(t, []).extend(recs)
+        for t, recs in mine.items():
+            recs.sort(key=lambda r: r[0])
+            states = [s for (st, s) in recs][::max(int(dump_step), 1)]
+            fn = os.path.join(self.out, "samples", "samples_replica%d_%d-%d.pickle" % (t + 1, first, last))
+            with open(fn, "wb") as f:
+                pickle.dump(states, f, protocol=2)
+        self._buffer = {}
+
+    def _write_stats(self):
+        if self.out is None or self.rank != 0:
+            return
+        p_acc = self.n_acc_T / np.maximum(self.n_hmc_T, 1)
+        row = [str(self.step)]
+        for t in range(self.T):
+            row += ["%.6f" % p_acc[t], "%.6e" % self.timestep_T[t]]
+        with open(os.path.join(self.out, "statistics", "mcmc_stats.txt"), "a") as f:
+            f.write("\t".join(row) + "\n")
+        re_rate = self.re_acc / np.maximum(self.re_try, 1)
+        with open(os.path.join(self.out, "statistics", "re_stats.txt"), "a") as f:
+            f.write("\t".join([str(self.step)] + ["%.6f" % v for v in re_rate[:max(self.T - 1, 0)]]) + "\n")
+        if self.works:
+            with open(os.path.join(self.out, "works", "works_%d.pickle" % self.step), "wb") as f:
+                pickle.dump(self.works, f, protocol=2)
+            self.works = []
+
+    def status_line(self):
+        p_acc = self.n_acc_T / np.maximum(self.n_hmc_T, 1)
+        re_rate = self.re_acc / np.maximum(self.re_try, 1)
+        return ("step %d  HMC p_acc %s  stepsize %s  RE p_acc %s"
+                % (self.step, np.array2string(p_acc, precision=2), np.array2string(self.timestep_T, precision=2),
+                   np.array2string(re_rate[:max(self.T - 1, 0)], precision=2)))
+
+    # ---- the loop (rexfw ExchangeMaster.run as driven by run_simulation.py:65-70) ----------------------------
+    def run(self, n_iterations, swap_interval=5, status_interval=100, dump_interval=250, dump_step=5,
+            statistics_update_interval=100, offset=0, verbose=False):
+        first = offset
+        for it in range(offset, offset + int(n_iterations)):
+            self.step = it
+            if it % int(swap_interval) == 0 and it > 0:
+                self.exchange()
+            else:
+                self.sample()
+            self._record()
+            if it % int(statistics_update_interval) == 0 and it > 0:
+                self._write_stats()
+            if verbose and self.rank == 0 and it % int(status_interval) == 0 and it > 0:
+                print(self.status_line(), flush=True)
+            if it % int(dump_interval) == 0 and it > 0:
+                self._dump(first, it, dump_step)
+                first = it
+        return self
+
+
+class ExchangeMaster(object):
+    """Object returned by setup_default_re_master: remembers the ladder size and output folder;
+    ``run`` mirrors ``master.run(n, swap_interval=..., ...)`` of run_simulation.py:65-70 once a
+    :class:`ReplicaExchange` has been bound."""
+
+    def __init__(self, n_replicas, sim_path):
+        self.n_replicas = n_replicas
+        self.sim_path = sim_path if sim_path.endswith("/") else sim_path + "/"
+        self.rex = None
+
+    def bind(self, rex):
+        self.rex = rex
+        return self
+
+    def run(self, n_iterations, swap_interval=5, status_interval=100, dump_interval=250, dump_step=5,
+            statistics_update_interval=100, offset=0, verbose=False):
+        if self.rex is None:
+            raise RuntimeError("bind() a ReplicaExchange first (see run_simulation.main)")
+        return self.rex.run(n_iterations, swap_interval, status_interval, dump_interval, dump_step,
+                            statistics_update_interval, offset, verbose)
+
+    def terminate_replicas(self):
+        pass
+
+
+def copy_run_metadata(config_file, schedule, output_folder):
+    """config.cfg and schedule.pickle next to the samples (run_simulation.py:56-59)"""
+    os.makedirs(output_folder, exist_ok=True)
+    shutil.copy2(config_file, os.path.join(output_folder, "config.cfg"))
+    with open(os.path.join(output_folder, "schedule.pickle"), "wb") as f:
+        pickle.dump({k: np.asarray(v) for k, v in schedule.items()}, f, protocol=2)

@@ -1,0 +1,54 @@
+"""Contact-list layout (host C++ inside the CUDA library, runs without a GPU): the canonical
+order the kernels walk is bit-exact, ragged and empty lists work, bad input is rejected."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import make_problem
+
+
+def _layout(N, data, exact=0):
+    from ensemble_hic_b200 import _lib
+    L = _lib.lib()
+    data = np.ascontiguousarray(data, dtype=np.int64).reshape(-1, 3)
+    M = len(data)
+    srt = np.zeros(max(M, 1), dtype=np.int64); ns = C.c_int64(); rl = np.zeros(N, dtype=np.int32)
+    rc = L.ehic_layout_debug(N, M, data.ctypes.data, exact, srt.ctypes.data, C.byref(ns), rl.ctypes.data)
+    return rc, srt[:M], ns.value, rl, L.ehic_last_error().decode()
+
+
+@pytest.mark.parametrize("exact", [0, 1])
+@pytest.mark.parametrize("seed,N,density", [(0, 40, 1.0), (1, 100, 0.2), (2, 23, 1.0), (3, 65, 0.05)])
+def test_sorted_contact_list_is_bitexact(seed, N, density, exact):
+    pb = make_problem(seed=seed, S=1, N=N, density=density)
+    data = pb["data"]
+    rc, srt, slots, rl, _ = _layout(N, data, exact)
+    assert rc == 0
+    expect = np.lexsort((np.arange(len(data)), data[:, 1], data[:, 0]))      # stable (i, j) order
+    assert np.array_equal(srt, expect)
+    deg = np.bincount(data[:, 0], minlength=N) + np.bincount(data[:, 1], minlength=N)
+    assert np.array_equal(rl, deg)
+    # sliced-ELL slots: 32 lanes x max row length per slice of 32 beads
+    exp_slots = sum(32 * int(deg[s:s + 32].max()) for s in range(0, N, 32))
+    assert slots == exp_slots
+
+
+def test_empty_and_tiny_lists():
+    rc, srt, slots, rl, _ = _layout(5, np.zeros((0, 3)))
+    assert rc == 0 and slots == 0 and not rl.any()
+    rc, srt, slots, rl, _ = _layout(2, [[1, 0, 7]])
+    assert rc == 0 and slots == 32 and list(rl) == [1, 1]
+
+
+def test_duplicate_pairs_keep_data_order():
+    data = [[0, 3, 1], [0, 3, 2], [2, 1, 5], [0, 3, 3]]
+    rc, srt, slots, rl, _ = _layout(4, data)
+    assert rc == 0 and list(srt) == [0, 1, 3, 2] and list(rl) == [3, 1, 1, 3]
+
+
+@pytest.mark.parametrize("bad,msg", [([[0, 5, 1]], "outside"), ([[-1, 2, 1]], "outside"), ([[2, 2, 1]], "itself")])
+def test_bad_indices_are_rejected(bad, msg):
+    from ensemble_hic_b200 import _lib
+    rc, _, _, _, err = _layout(5, bad)
+    assert rc == _lib.ERR_INVALID and msg in err
