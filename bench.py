@@ -290,6 +290,32 @@ def run_b200(args):
     e2e_value = n_total * n_e2e / float(dt.item())
     bytes_x = R * S * N * 3 * 8
 
+    # ---- replica-exchange sweeps / s (second half of BASELINE.json's metric) ----------------------
+    # one sweep = one iteration of the whole ladder: every replica draws one Gibbs sample (HMC
+    # trajectory of L = 100 leapfrog steps = 101 gradients + 2 energies, then the norm draw with one
+    # forward-model evaluation); every 5th iteration is an exchange round instead (swap_interval = 5).
+    sweeps = None
+    if args.sweeps > 0:
+        from ensemble_hic_b200.rex import EngineBackend, ReplicaExchange
+        lad_all = ladder(n_total)
+        rex = ReplicaExchange(EngineBackend(model), {"lammda": lad_all, "beta": lad_all}, pb["X"].reshape(R, -1),
+                              norm.cpu().numpy(), dict(timestep=1e-4, trajectory_length=100, adaption_limit=0),
+                              norm_prior=(float(np.mean(counts[counts > 0])) / S, 1.0 / S), counts_sum=float(counts.sum()),
+                              output_folder=None, seed=0, rank=rank, world_size=world, dist=dist if world > 1 else None,
+                              momenta="torch")
+        rex.run(1, swap_interval=5, offset=1)                       # warm-up: one sample
+        barrier()
+        t0 = time.perf_counter()
+        rex.run(args.sweeps, swap_interval=5, offset=6 - args.sweeps + 0)   # ends with the exchange round at it = 5
+        barrier()
+        dts = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dts, op=dist.ReduceOp.MAX)
+        sweeps = {"value": args.sweeps / float(dts.item()), "unit": "RE sweeps/s (whole ladder of %d replicas)" % n_total,
+                  "iterations": args.sweeps, "trajectory_length": 100, "swap_interval": 5,
+                  "hmc_acceptance": float(np.mean(rex.n_acc_T / np.maximum(rex.n_hmc_T, 1))),
+                  "replica_trajectories_per_s": n_total * (args.sweeps - 1) / float(dts.item())}
+
     # ---- per-kernel durations (CUDA events on the launching stream, same call sequence) ------
     kern = None
     if rank == 0:
@@ -341,7 +367,7 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_x + 3 * R * 8,
                         "d2h_bytes_per_step": bytes_x,
                         "api": "ehic_evaluate_host (C ABI) with pinned host buffers, batched over the GPU's replicas"},
-                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu}
+                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "re_sweeps": sweeps}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -355,6 +381,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweeps", type=int, default=5, help="RE iterations timed for the sweeps/s figure (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
