@@ -48,6 +48,11 @@ struct ehic_model {
     int max_replicas = 0;
     DevModel dm{};
     ContactLayout layout;           // host copy (sizes, perm)
+    bool use_tiles = false;         // dense list + fast mode: symmetric tile path
+    TileDev td{};
+    double tile_fill = 0.0;
+    int nA_tile = 0, nKc = 0;       // forward-tile blocks per replica; combine blocks per structure
+    double *tw = nullptr, *Grow = nullptr, *Pbuf = nullptr;
     std::vector<void *> owned;      // device allocations
     // workspace
     double *xs[2] = {nullptr, nullptr};   // SoA working copies (forward + prior kernels)
@@ -57,6 +62,7 @@ struct ehic_model {
     double *energies = nullptr, *kinetic = nullptr;
     int nA = 0;                     // forward blocks per replica
     int nPx = 0;                    // prior blocks per structure
+    int cur_xt = 0;                 // which xt buffer matches the xs buffer handed to launch_forward
     int kt = 1, nkt = 1, nktg = 1;  // structures per warp, tiles per replica, tile groups (gw warps) per slice
     int gw = 4;                     // warps per gather CTA
     double r_max = 0.0;
@@ -213,6 +219,18 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     dm.sph_R = desc->sphere_radius; dm.sph_k = desc->sphere_k;
     dm.sph_cx = desc->sphere_center[0]; dm.sph_cy = desc->sphere_center[1]; dm.sph_cz = desc->sphere_center[2];
 
+    // dense lists in fast mode take the symmetric tile path (EHIC_PATH=rows|tiles overrides)
+    TileLayout TL;
+    {
+        const char *path = getenv("EHIC_PATH");
+        const char *mf = getenv("EHIC_TILE_MIN_FILL");
+        double min_fill = mf ? atof(mf) : 0.5;
+        bool want = !exact && !(path && !strcmp(path, "rows"));
+        if (path && !strcmp(path, "tiles")) min_fill = 0.0;
+        if (want && desc->n_data > 0) build_tiles(L, desc->data_points, desc->contact_distances, min_fill, TL);
+        m->use_tiles = TL.eligible;
+        m->tile_fill = TL.fill;
+    }
     std::vector<long long> perm(L.perm.begin(), L.perm.end()), soff(L.slice_off.begin(), L.slice_off.end());
 #define UP(vec, field)                                              \
     do { rc = upload(m, vec, &dm.field); if (rc) { ehic_model_destroy(m); return rc; } } while (0)
@@ -221,6 +239,18 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     UP(soff, slice_off); UP(L.slice_w, slice_w); UP(L.ent_j, ent_j); UP(L.ent_dc, ent_dc);
     UP(radii, radii); UP(ul, bb_ul); UP(ll, bb_ll);
 #undef UP
+    if (m->use_tiles) {
+        TileDev &td = m->td;
+        td.n_rb = TL.n_rb; td.n_tiles = TL.n_tiles; td.n_sub = (int)TL.sub_tile.size(); td.n_sl = L.n_slices;
+        td.slots = (long long)TL.n_tiles * 4096;
+        std::vector<long long> orig(TL.orig.begin(), TL.orig.end());
+#define UPT(vec, field)                                             \
+    do { rc = upload(m, vec, &td.field); if (rc) { ehic_model_destroy(m); return rc; } } while (0)
+        UPT(TL.tile_I, tile_I); UPT(TL.tile_B, tile_B); UPT(TL.rb_begin, rb_begin);
+        UPT(TL.sub_tile, sub_tile); UPT(TL.sub_rb, sub_rb); UPT(TL.exists, exists);
+        UPT(TL.mask, mask); UPT(TL.dc, dc); UPT(TL.cnt, cnt); UPT(orig, orig);
+#undef UPT
+    }
     // free the big host vectors we no longer need
     std::vector<int32_t>().swap(L.ent_j); std::vector<double>().swap(L.ent_dc);
     std::vector<int32_t>().swap(L.slot_a); std::vector<int32_t>().swap(L.slot_b);
@@ -247,6 +277,19 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     DA(m->partP, Rm * (size_t)S * m->nPx * 3);
     DA(m->partK, Rm * (size_t)L.n_slices * m->nktg * m->gw);
     DA(m->energies, Rm * 4); DA(m->kinetic, Rm);
+    if (m->use_tiles) {
+        m->nA_tile = (2 * m->td.n_sub + 3) / 4;                       // QC = 16: two items per sub-tile
+        m->nKc = (N + 255) / 256;
+        DA(m->tw, Rm * (size_t)m->td.slots);
+        DA(m->Grow, Rm * S * (size_t)N * 3);
+        DA(m->Pbuf, Rm * S * (size_t)m->td.n_rb * N * 3);
+        double *pa2 = nullptr, *pk2 = nullptr;                         // partials sized for the tile kernels
+        DA(pa2, Rm * (size_t)std::max(std::max(m->nA_tile, m->nA), 1)); m->partA = pa2;
+        DA(pk2, Rm * (size_t)std::max<size_t>((size_t)S * m->nKc, (size_t)L.n_slices * m->nktg * m->gw)); m->partK = pk2;
+        if (cudaMemset(m->tw, 0, Rm * (size_t)m->td.slots * sizeof(double)) != cudaSuccess) {
+            ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed");
+        }
+    }
 #undef DA
     // weights of padding slots are never read (ent_j < 0), but keep the buffer defined
     if (cudaMemset(m->wbuf, 0, Rm * (size_t)dm.wstride * sizeof(double)) != cudaSuccess) {
@@ -308,7 +351,7 @@ int ehic_model_info(const ehic_model_t *m, int64_t out[8])
 {
     if (!m || !out) return fail(EHIC_ERR_INVALID, "null argument");
     out[0] = m->dm.N; out[1] = m->dm.S; out[2] = m->dm.M; out[3] = m->max_replicas;
-    out[4] = m->flags; out[5] = m->dm.tot; out[6] = m->device; out[7] = m->kt * 100 + m->gw;
+    out[4] = m->flags; out[5] = m->dm.tot; out[6] = m->device; out[7] = m->kt * 100 + m->gw + (m->use_tiles ? 10000 : 0);
     return EHIC_OK;
 }
 
@@ -341,8 +384,20 @@ static int launch_forward(ehic_model *m, int R, const double *xs, const double *
         if (want_logl) CU(cudaMemsetAsync(m->partA, 0, sizeof(double) * (size_t)R * std::max(m->nA, 1), st));
         return EHIC_OK;
     }
-    dim3 grid((unsigned)m->nA, (unsigned)R);
     KernelTimer kt_(m, KC_FORWARD, st);
+    if (m->use_tiles) {
+        dim3 gridt((unsigned)m->nA_tile, (unsigned)R);
+        double *twp = want_w ? m->tw : nullptr;
+        switch (m->kt) {
+        case 4: forward_tile_kernel<4, 16><<<gridt, 128, 0, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_md, twp, m->partA, want_logl, m->nkt); break;
+        case 2: forward_tile_kernel<2, 16><<<gridt, 128, 0, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_md, twp, m->partA, want_logl, m->nkt); break;
+        default: forward_tile_kernel<1, 16><<<gridt, 128, 0, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_md, twp, m->partA, want_logl, m->nkt); break;
+        }
+        LAUNCHED();
+        CU(cudaGetLastError());
+        return EHIC_OK;
+    }
+    dim3 grid((unsigned)m->nA, (unsigned)R);
     if (m->flags & EHIC_FLAG_EXACT)
         forward_kernel<true><<<grid, 256, 0, st>>>(m->dm, xs, d_norm, d_md, want_w ? m->wbuf : nullptr, m->partA, want_logl);
     else
@@ -382,6 +437,21 @@ static void launch_gather_t(ehic_model *m, const GatherArgs &ga, int R, cudaStre
 
 static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_t st)
 {
+    if (m->use_tiles) {
+        if (ga.contact) {
+            KernelTimer kt_(m, KC_GATHER, st);
+            long long items = (long long)R * m->dm.S * m->td.n_rb;
+            backward_tile_kernel<<<(unsigned)((items + 3) / 4), 128, 0, st>>>(m->dm, m->td, ga.xs_cur, m->tw, m->Grow, m->Pbuf, items);
+            LAUNCHED();
+            CU(cudaGetLastError());
+        }
+        KernelTimer kt2_(m, KC_OTHER, st);
+        dim3 grid((unsigned)m->nKc, (unsigned)m->dm.S, (unsigned)R);
+        combine_kernel<<<grid, 256, 0, st>>>(m->dm, m->td, ga, m->Grow, m->Pbuf, ga.contact, m->kt, m->nkt);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        return EHIC_OK;
+    }
     KernelTimer kt_(m, KC_GATHER, st);
     if (m->flags & EHIC_FLAG_EXACT) launch_gather_t<true>(m, ga, R, st);
     else launch_gather_t<false>(m, ga, R, st);
@@ -393,9 +463,10 @@ static int launch_finalize(ehic_model *m, int R, bool haveA, bool haveP, bool ha
                            double *d_energies, double *d_kin, cudaStream_t st)
 {
     KernelTimer kt_(m, KC_FINALIZE, st);
-    finalize_kernel<<<R, 256, 0, st>>>(m->dm, haveA ? m->partA : nullptr, m->nA,
+    finalize_kernel<<<R, 256, 0, st>>>(m->dm, haveA ? m->partA : nullptr, m->use_tiles ? m->nA_tile : m->nA,
                                        haveP ? m->partP : nullptr, (long long)m->dm.S * m->nPx,
-                                       haveK ? m->partK : nullptr, (long long)m->dm.n_slices * m->nktg * m->gw,
+                                       haveK ? m->partK : nullptr,
+                                       m->use_tiles ? (long long)m->dm.S * m->nKc : (long long)m->dm.n_slices * m->nktg * m->gw,
                                        d_energies, d_kin);
     LAUNCHED();
     CU(cudaGetLastError());
@@ -412,8 +483,9 @@ int ehic_mock_data(ehic_model_t *m, int R, const double *d_x, const double *d_no
     if (rc) return rc;
     if (!d_x || !d_norm || !d_md) return fail(EHIC_ERR_INVALID, "null buffer");
     cudaStream_t st = (cudaStream_t)stream;
-    rc = launch_pack(m, R, d_x, m->xs[0], nullptr, st);
+    rc = launch_pack(m, R, d_x, m->xs[0], m->use_tiles ? m->xt[0] : nullptr, st);
     if (rc) return rc;
+    m->cur_xt = 0;
     return launch_forward(m, R, m->xs[0], d_norm, d_md, false, false, st);
 }
 
@@ -430,8 +502,9 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     const int prior_terms = terms & ~EHIC_TERM_LIKELIHOOD;
     if ((lik || d_md) && !d_norm) return fail(EHIC_ERR_INVALID, "norm required for the likelihood term");
     cudaStream_t st = (cudaStream_t)stream;
-    rc = launch_pack(m, R, d_x, m->xs[0], d_grad ? m->xt[0] : nullptr, st);
+    rc = launch_pack(m, R, d_x, m->xs[0], (d_grad || m->use_tiles) ? m->xt[0] : nullptr, st);
     if (rc) return rc;
+    m->cur_xt = 0;
     const bool need_forward = (lik && (d_grad || d_energies)) || d_md;
     if (need_forward) {
         rc = launch_forward(m, R, m->xs[0], d_norm, d_md, lik && d_grad, lik && d_energies, st);
@@ -444,7 +517,7 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     }
     if (d_grad) {
         GatherArgs ga{};
-        ga.xt = m->xt[0]; ga.wbuf = m->wbuf; ga.lammda = d_lammda;
+        ga.xt = m->xt[0]; ga.xs_cur = m->xs[0]; ga.wbuf = m->wbuf; ga.lammda = d_lammda;
         ga.gprior = need_prior ? m->gprior : nullptr;
         ga.grad = d_grad; ga.contact = lik ? 1 : 0;
         rc = launch_gather(m, ga, R, st);
@@ -474,12 +547,13 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
     for (int s = 0; s <= n_steps; s++) {
         const bool first = (s == 0), last = (s == n_steps);
         const bool ends = first || last;
+        m->cur_xt = cur;
         rc = launch_forward(m, R, m->xs[cur], d_norm, nullptr, true, ends, st);
         if (rc) return rc;
         rc = launch_prior(m, R, prior_terms, m->xs[cur], d_beta, true, ends, st);
         if (rc) return rc;
         GatherArgs ga{};
-        ga.xt = m->xt[cur]; ga.wbuf = m->wbuf; ga.lammda = d_lammda; ga.gprior = m->gprior;
+        ga.xt = m->xt[cur]; ga.xs_cur = m->xs[cur]; ga.wbuf = m->wbuf; ga.lammda = d_lammda; ga.gprior = m->gprior;
         ga.grad = nullptr; ga.partK = ends ? m->partK : nullptr; ga.contact = 1;
         ga.p = d_p; ga.eps = d_eps; ga.kick = ends ? 0.5 : 1.0;
         ga.xs_next = last ? nullptr : m->xs[cur ^ 1];

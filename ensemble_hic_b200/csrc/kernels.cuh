@@ -413,6 +413,7 @@ struct GatherArgs {
     double kick;            // 0.5 or 1.0
     double *xs_next;        // [R][S][3][Np]: x + eps * p (after the kick), or NULL (no drift)
     double *xt_next;        // the same in tile-AoS layout
+    const double *xs_cur;   // [R][S][3][Np] current positions (SoA), read by combine_kernel for the drift
     int kinetic_mode;       // partK = sum p^2 before the kick (1) / after the kick (2) / none (0)
 };
 
@@ -557,6 +558,258 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
     if (ga.partK) {
         kin = warp_sum(kin);
         if (lane == 0) ga.partK[(long long)blockIdx.x * n_warps + warp] = kin;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// TILE path (dense contact lists, fast arithmetic): every unordered bead pair is evaluated ONCE
+// in the backward pass.  See layout.hpp (3) for the slot geometry.
+struct TileDev {
+    int n_rb, n_tiles, n_sub, n_sl;
+    const int *tile_I, *tile_B, *rb_begin, *sub_tile, *sub_rb, *exists;
+    const unsigned *mask;
+    const double *dc, *cnt;
+    const long long *orig;
+    long long slots;          // n_tiles * 4096: per-replica stride of the tile weights
+};
+
+// Forward, tile form: warp <-> (replica, non-empty 32 x 32 sub-tile, group of QC columns); lane <->
+// row bead.  Column beads are warp-uniform (broadcast LDG.128 of tile-AoS records), the S
+// structures are walked in order with one accumulator per column: no cross-lane reduction and the
+// reference's summation order over the ensemble.  Writes md (data_points order), the Poisson
+// weight of every present slot, and per-block partials of log L.
+template <int KT, int QC>
+__global__ void __launch_bounds__(128)
+forward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xt, const double *__restrict__ norm,
+                    double *__restrict__ md_out, double *__restrict__ tw, double *__restrict__ partA,
+                    int want_logl, int nkt)
+{
+    // grid = (blocks per replica, R); 4 warps per block, one item each
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int HALVES = 32 / QC;
+    const int item = blockIdx.x * 4 + warp;
+    const int r = blockIdx.y;
+    double term = 0.0;
+    if (item < HALVES * td.n_sub) {
+        const int h = item % HALVES;
+        const int sub = item / HALVES;
+        const int tile = td.sub_tile[sub], rb = td.sub_rb[sub];
+        const int I = td.tile_I[tile], B = td.tile_B[tile];
+        const int bA = min((4 * I + rb) * 32 + lane, dm.N - 1);
+        const int col0 = 32 * B + h * QC;
+        const unsigned mask = td.mask[((long long)tile * 4 + rb) * 32 + lane] >> (h * QC);
+        const long long pos0 = (((long long)tile * 32 + h * QC) * 4 + rb) * 32 + lane;
+        const double alpha = dm.alpha;
+        const int Np = dm.Np;
+        double acc[QC];
+#pragma unroll
+        for (int q = 0; q < QC; q++) acc[q] = 0.0;
+        const double *recs = xt + (long long)r * nkt * Np * (KT * 3);
+        auto body = [&](int kt, int nvalid) {
+            double own[KT * 3];
+            load_record<KT>(recs + ((long long)kt * Np + bA) * (KT * 3), own);
+#pragma unroll
+            for (int q = 0; q < QC; q++) {
+                const int oc = min(col0 + q, dm.N - 1);
+                double v[KT * 3];
+                load_record<KT>(recs + ((long long)kt * Np + oc) * (KT * 3), v);
+                const double dc = td.dc[pos0 + q * 128];
+#pragma unroll
+                for (int t = 0; t < KT; t++) {
+                    if (t < nvalid) {
+                        double dx = v[3 * t] - own[3 * t], dy = v[3 * t + 1] - own[3 * t + 1], dz = v[3 * t + 2] - own[3 * t + 2];
+                        double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                        double rd = rsqrt_nr(s2);
+                        double tt = alpha * (dc - s2 * rd);
+                        double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                        acc[q] += fma(tt, rq, 1.0);
+                    }
+                }
+            }
+        };
+        const int nfull = dm.S / KT;
+        for (int kt = 0; kt < nfull; kt++) body(kt, KT);
+        if (nfull < nkt) body(nfull, dm.S - nfull * KT);
+        const double nrm = norm[r];
+#pragma unroll
+        for (int q = 0; q < QC; q++) {
+            if ((mask >> q) & 1u) {
+                const long long pos = pos0 + q * 128;
+                const double md = acc[q] * (0.5 * nrm);
+                const double c = td.cnt[pos];
+                if (md_out) md_out[(long long)r * dm.M + td.orig[pos]] = md;
+                if (tw) {
+                    double em = __dsub_rn(1.0, __ddiv_rn(c, md));
+                    tw[(long long)r * td.slots + pos] = __dmul_rn(__dmul_rn(__dmul_rn(0.5, em), nrm), alpha);
+                }
+                if (want_logl) term += c * log(md) - md;
+            }
+        }
+    }
+    if (want_logl) {
+        __shared__ double sh[4];
+        double v = warp_sum(term);
+        if (lane == 0) sh[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) partA[(long long)r * gridDim.x + blockIdx.x] = (sh[0] + sh[1]) + (sh[2] + sh[3]);
+    }
+}
+
+// Halving butterfly: 8 per-lane values -> the warp-wide sums of the 8 columns; after the call
+// r[0] of lane L is the total of column ((L>>2)&1) + 2*((L>>3)&1) + 4*((L>>4)&1).
+// 9 shuffle-adds instead of 40; fixed order (deterministic).
+__device__ __forceinline__ void reduce8(double (&r)[8], int lane)
+{
+    bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double send = hi ? r[i] : r[i + 4], keep = hi ? r[i + 4] : r[i];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    hi = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        double send = hi ? r[i] : r[i + 2], keep = hi ? r[i + 2] : r[i];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    hi = (lane & 4) != 0;
+    {
+        double send = hi ? r[0] : r[1], keep = hi ? r[1] : r[0];
+        r[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    r[0] += __shfl_xor_sync(0xffffffffu, r[0], 2);
+    r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+}
+
+// Backward, tile form: warp <-> (replica, structure, row block of 128 beads); each lane owns 4 row
+// beads (accumulated in registers over all column slices of the row block) and, per group of 8
+// warp-uniform column beads, the partial reactions, which are summed over the warp with reduce8
+// and written to the per-row-block partial buffer P[r][k][I][bead][3].  No atomics.
+__global__ void __launch_bounds__(128)
+backward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xs, const double *__restrict__ tw,
+                     double *__restrict__ Grow, double *__restrict__ P, long long n_items)
+{
+    const int lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (item >= n_items) return;
+    const int I = (int)(item % td.n_rb);
+    const long long rk = item / td.n_rb;            // r * S + k
+    const int r = (int)(rk / dm.S);
+    const int Np = dm.Np;
+    const double *xk = xs + rk * 3LL * Np;
+    const double alpha = dm.alpha;
+    int bA[4];
+    double xb[4][3], acc[4][3];
+#pragma unroll
+    for (int rb = 0; rb < 4; rb++) {
+        bA[rb] = min((4 * I + rb) * 32 + lane, dm.N - 1);
+        xb[rb][0] = xk[bA[rb]]; xb[rb][1] = xk[Np + bA[rb]]; xb[rb][2] = xk[2 * Np + bA[rb]];
+        acc[rb][0] = acc[rb][1] = acc[rb][2] = 0.0;
+    }
+    const double *twr = tw + (long long)r * td.slots;
+    double *Pk = P + (rk * td.n_rb + I) * (long long)dm.N * 3;
+    for (int t = td.rb_begin[I]; t < td.rb_begin[I + 1]; t++) {
+        const int col0 = 32 * td.tile_B[t];
+        unsigned m[4];
+#pragma unroll
+        for (int rb = 0; rb < 4; rb++) m[rb] = td.mask[((long long)t * 4 + rb) * 32 + lane];
+        const long long tbase = (long long)t * 4096 + lane;
+        for (int qg = 0; qg < 4; qg++) {
+            double rx[8], ry[8], rz[8];
+#pragma unroll
+            for (int qq = 0; qq < 8; qq++) {
+                const int q = qg * 8 + qq;
+                const int oc = min(col0 + q, dm.N - 1);
+                const double ox = xk[oc], oy = xk[Np + oc], oz = xk[2 * Np + oc];
+                double fx = 0.0, fy = 0.0, fz = 0.0;
+#pragma unroll
+                for (int rb = 0; rb < 4; rb++) {
+                    const long long pos = tbase + (q * 4 + rb) * 32;
+                    const double dc = td.dc[pos], w = twr[pos];
+                    double dx = ox - xb[rb][0], dy = oy - xb[rb][1], dz = oz - xb[rb][2];
+                    double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    double rd = rsqrt_nr(s2);
+                    double tt = alpha * (dc - s2 * rd);
+                    double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                    double f = w * ((rq * rq) * (rq * rd));
+                    f = ((m[rb] >> q) & 1u) ? f : 0.0;
+                    acc[rb][0] = fma(f, dx, acc[rb][0]); acc[rb][1] = fma(f, dy, acc[rb][1]); acc[rb][2] = fma(f, dz, acc[rb][2]);
+                    fx = fma(-f, dx, fx); fy = fma(-f, dy, fy); fz = fma(-f, dz, fz);
+                }
+                rx[qq] = fx; ry[qq] = fy; rz[qq] = fz;
+            }
+            reduce8(rx, lane); reduce8(ry, lane); reduce8(rz, lane);
+            if ((lane & 3) == 0) {
+                const int col = col0 + qg * 8 + (((lane >> 2) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 4) & 1));
+                if (col < dm.N) { double *o = Pk + (long long)col * 3; o[0] = rx[0]; o[1] = ry[0]; o[2] = rz[0]; }
+            }
+        }
+    }
+#pragma unroll
+    for (int rb = 0; rb < 4; rb++) {
+        const int b = (4 * I + rb) * 32 + lane;
+        if (b < dm.N) { double *o = Grow + (rk * dm.N + b) * 3; o[0] = acc[rb][0]; o[1] = acc[rb][1]; o[2] = acc[rb][2]; }
+    }
+}
+
+// Combine + epilogue of the tile path: thread <-> (replica, structure, bead).
+// g = lammda * (row sum + sum over row blocks of the reaction partials, ascending) + gprior,
+// then the same leapfrog epilogue as gather_kernel.
+__global__ void __launch_bounds__(256)
+combine_kernel(DevModel dm, TileDev td, GatherArgs ga, const double *__restrict__ Grow, const double *__restrict__ P,
+               int contact, int KT, int nkt)
+{
+    const int k = blockIdx.y, r = blockIdx.z;
+    const int b = blockIdx.x * 256 + threadIdx.x;
+    const long long rk = (long long)r * dm.S + k;
+    double kin = 0.0;
+    if (b < dm.N) {
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+        const long long at = (rk * dm.N + b) * 3;
+        if (contact) {
+            g0 = Grow[at]; g1 = Grow[at + 1]; g2 = Grow[at + 2];
+            const int sl = b >> 5;
+            for (int I = 0; I <= (sl >> 2); I++) {
+                if (td.exists[I * td.n_sl + sl] >= 0) {
+                    const double *o = P + ((rk * td.n_rb + I) * (long long)dm.N + b) * 3;
+                    g0 += o[0]; g1 += o[1]; g2 += o[2];
+                }
+            }
+        }
+        const double lam = ga.lammda ? ga.lammda[r] : 1.0;
+        g0 *= lam; g1 *= lam; g2 *= lam;
+        if (ga.gprior) { g0 += ga.gprior[at]; g1 += ga.gprior[at + 1]; g2 += ga.gprior[at + 2]; }
+        if (ga.grad) { ga.grad[at] = g0; ga.grad[at + 1] = g1; ga.grad[at + 2] = g2; }
+        if (ga.p) {
+            const double eps = ga.eps[r];
+            double p0 = ga.p[at], p1 = ga.p[at + 1], p2 = ga.p[at + 2];
+            if (ga.kinetic_mode == 1) kin = p0 * p0 + p1 * p1 + p2 * p2;
+            const double ke = ga.kick * eps;
+            p0 = fma(-ke, g0, p0); p1 = fma(-ke, g1, p1); p2 = fma(-ke, g2, p2);
+            ga.p[at] = p0; ga.p[at + 1] = p1; ga.p[at + 2] = p2;
+            if (ga.kinetic_mode == 2) kin = p0 * p0 + p1 * p1 + p2 * p2;
+            if (ga.xs_next) {
+                const int Np = dm.Np;
+                const double *xc = ga.xs_cur + rk * 3LL * Np;
+                const double n0 = fma(eps, p0, xc[b]), n1 = fma(eps, p1, xc[Np + b]), n2 = fma(eps, p2, xc[2 * Np + b]);
+                double *xn = ga.xs_next + rk * 3LL * Np;
+                xn[b] = n0; xn[Np + b] = n1; xn[2 * Np + b] = n2;
+                double *un = ga.xt_next + ((((long long)r * nkt + k / KT) * Np + b) * KT + (k % KT)) * 3;
+                un[0] = n0; un[1] = n1; un[2] = n2;
+            }
+        }
+    }
+    if (ga.partK) {
+        __shared__ double sh[8];
+        double v = warp_sum(kin);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) t += sh[q];
+            ga.partK[rk * gridDim.x + blockIdx.x] = t;
+        }
     }
 }
 

@@ -19,6 +19,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <string>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -43,6 +44,76 @@ struct ContactLayout {
     int64_t tot = 0;                  // slots that belong to slices (multiple of 32)
     static constexpr int64_t kTailPad = 16 * 32;   // so a 16-entry chunk copy never leaves the array
 };
+
+// (3) TILE view (dense lists only): every unordered pair {lo < hi} once, in the tile
+//     (row block I = lo / 128, column slice B = hi / 32); a tile is 128 row beads x 32 column
+//     beads = 4096 slots, slot = ((tile*32 + q)*4 + rb)*32 + lane with q = hi % 32,
+//     rb = (lo / 32) % 4, lane = lo % 32.  The symmetric backward kernel walks the tiles of a row
+//     block and accumulates action (row bead, registers) and reaction (column bead, warp
+//     shuffles); the forward kernel walks the non-empty 32 x 32 sub-tiles (tile, rb).
+struct TileLayout {
+    bool eligible = false;          // dense enough, no duplicate pairs
+    std::string why;                // reason when not eligible
+    int32_t n_rb = 0;               // row blocks (128 beads)
+    int32_t n_tiles = 0;
+    std::vector<int32_t> tile_I, tile_B;      // n_tiles, sorted by (I, B)
+    std::vector<int32_t> rb_begin;            // n_rb + 1: tile range of each row block
+    std::vector<int32_t> sub_tile, sub_rb;    // non-empty 32x32 sub-tiles
+    std::vector<uint32_t> mask;               // [n_tiles][4][32]: bit q = slot (q, rb, lane) present
+    std::vector<double> dc, cnt;              // [n_tiles*4096]
+    std::vector<int64_t> orig;                // [n_tiles*4096] row of data_points, -1 = absent
+    std::vector<int32_t> exists;              // [n_rb][n_slices]: tile index or -1
+    double fill = 0.0;
+};
+
+inline void build_tiles(const ContactLayout &L, const int64_t *data, const double *cds, double min_fill, TileLayout &T)
+{
+    T = TileLayout();
+    const int32_t N = L.N; const int64_t M = L.M;
+    if (M == 0 || N < 64) { T.why = "list too small"; return; }
+    const int32_t n_sl = (N + 31) / 32;
+    T.n_rb = (n_sl + 3) / 4;
+    std::vector<int32_t> id((size_t)T.n_rb * n_sl, -1);
+    std::vector<int64_t> per_tile((size_t)T.n_rb * n_sl, 0);
+    for (int64_t m = 0; m < M; m++) {
+        int64_t i = data[3 * m], j = data[3 * m + 1];
+        int64_t lo = std::min(i, j), hi = std::max(i, j);
+        per_tile[(lo / 128) * n_sl + hi / 32]++;
+    }
+    for (int32_t I = 0; I < T.n_rb; I++) {
+        T.rb_begin.push_back(T.n_tiles);
+        for (int32_t B = 0; B < n_sl; B++)
+            if (per_tile[(size_t)I * n_sl + B] > 0) {
+                id[(size_t)I * n_sl + B] = T.n_tiles++;
+                T.tile_I.push_back(I); T.tile_B.push_back(B);
+            }
+    }
+    T.rb_begin.push_back(T.n_tiles);
+    T.fill = (double)M / ((double)T.n_tiles * 4096.0);
+    if (T.fill < min_fill) { T.why = "tile fill below threshold"; return; }
+    if ((int64_t)T.n_tiles * 4096 >= ((int64_t)1 << 31)) { T.why = "too many tile slots"; return; }
+    const size_t slots = (size_t)T.n_tiles * 4096;
+    T.mask.assign((size_t)T.n_tiles * 128, 0u);
+    T.dc.assign(slots, 0.0); T.cnt.assign(slots, 0.0); T.orig.assign(slots, -1);
+    for (int64_t m = 0; m < M; m++) {
+        int64_t i = data[3 * m], j = data[3 * m + 1];
+        int64_t lo = std::min(i, j), hi = std::max(i, j);
+        int32_t t = id[(lo / 128) * n_sl + hi / 32];
+        int32_t q = (int32_t)(hi % 32), rb = (int32_t)((lo / 32) % 4), lane = (int32_t)(lo % 32);
+        size_t pos = (((size_t)t * 32 + q) * 4 + rb) * 32 + lane;
+        if (T.orig[pos] >= 0) { T.why = "duplicate data points for one bead pair"; return; }
+        T.orig[pos] = m; T.dc[pos] = cds[m]; T.cnt[pos] = (double)data[3 * m + 2];
+        T.mask[((size_t)t * 4 + rb) * 32 + lane] |= (1u << q);
+    }
+    for (int32_t t = 0; t < T.n_tiles; t++)
+        for (int32_t rb = 0; rb < 4; rb++) {
+            uint32_t any = 0;
+            for (int32_t lane = 0; lane < 32; lane++) any |= T.mask[((size_t)t * 4 + rb) * 32 + lane];
+            if (any) { T.sub_tile.push_back(t); T.sub_rb.push_back(rb); }
+        }
+    T.exists = id;
+    T.eligible = true;
+}
 
 // Returns "" on success, otherwise an error message.
 inline std::string build_layout(int32_t N, int64_t M, const int64_t *data, const double *cds,
