@@ -86,6 +86,11 @@ KernelTimer::KernelTimer(ehic_model *m_, int cls, cudaStream_t st_) : m(m_), st(
 }
 KernelTimer::~KernelTimer() { if (idx >= 0) cudaEventRecord(m->timed[idx].b, st); }
 
+static size_t forward_tile_smem(int kt)
+{
+    return sizeof(double) * (4096 + (size_t)EHIC_FT_STAGES * (128 + 32) * kt * 3);
+}
+
 template <typename T>
 static int upload(ehic_model *m, const std::vector<T> &v, const T **out)
 {
@@ -278,7 +283,7 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     DA(m->partK, Rm * (size_t)L.n_slices * m->nktg * m->gw);
     DA(m->energies, Rm * 4); DA(m->kinetic, Rm);
     if (m->use_tiles) {
-        m->nA_tile = (2 * m->td.n_sub + 3) / 4;                       // QC = 16: two items per sub-tile
+        m->nA_tile = m->td.n_tiles;                                   // one forward CTA (partial) per tile
         m->nKc = (N + 255) / 256;
         DA(m->tw, Rm * (size_t)m->td.slots);
         DA(m->Grow, Rm * S * (size_t)N * 3);
@@ -289,6 +294,17 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         if (cudaMemset(m->tw, 0, Rm * (size_t)m->td.slots * sizeof(double)) != cudaSuccess) {
             ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed");
         }
+        // both tile kernels use more than the 48 KB of static shared memory
+        cudaError_t e1 = cudaFuncSetAttribute(backward_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(EHIC_BT_STAGES * 2048 * sizeof(double)));
+        cudaError_t e2 = cudaSuccess;
+        const int fsm = (int)forward_tile_smem(m->kt);
+        switch (m->kt) {
+        case 4: e2 = cudaFuncSetAttribute(forward_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm); break;
+        case 2: e2 = cudaFuncSetAttribute(forward_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm); break;
+        default: e2 = cudaFuncSetAttribute(forward_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm); break;
+        }
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaFuncSetAttribute failed"); }
     }
 #undef DA
     // weights of padding slots are never read (ent_j < 0), but keep the buffer defined
@@ -386,12 +402,13 @@ static int launch_forward(ehic_model *m, int R, const double *xs, const double *
     }
     KernelTimer kt_(m, KC_FORWARD, st);
     if (m->use_tiles) {
-        dim3 gridt((unsigned)m->nA_tile, (unsigned)R);
+        dim3 gridt((unsigned)m->td.n_tiles, (unsigned)R);
         double *twp = want_w ? m->tw : nullptr;
+        const size_t sm = forward_tile_smem(m->kt);
         switch (m->kt) {
-        case 4: forward_tile_kernel<4, 16><<<gridt, 128, 0, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_md, twp, m->partA, want_logl, m->nkt); break;
-        case 2: forward_tile_kernel<2, 16><<<gridt, 128, 0, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_md, twp, m->partA, want_logl, m->nkt); break;
-        default: forward_tile_kernel<1, 16><<<gridt, 128, 0, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_md, twp, m->partA, want_logl, m->nkt); break;
+        case 4: forward_tile_kernel<4><<<gridt, 256, sm, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_md, twp, m->partA, want_logl, m->nkt); break;
+        case 2: forward_tile_kernel<2><<<gridt, 256, sm, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_md, twp, m->partA, want_logl, m->nkt); break;
+        default: forward_tile_kernel<1><<<gridt, 256, sm, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_md, twp, m->partA, want_logl, m->nkt); break;
         }
         LAUNCHED();
         CU(cudaGetLastError());
@@ -440,8 +457,9 @@ static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_
     if (m->use_tiles) {
         if (ga.contact) {
             KernelTimer kt_(m, KC_GATHER, st);
-            long long items = (long long)R * m->dm.S * m->td.n_rb;
-            backward_tile_kernel<<<(unsigned)((items + 3) / 4), 128, 0, st>>>(m->dm, m->td, ga.xs_cur, m->tw, m->Grow, m->Pbuf, items);
+            const int n_kg = (m->dm.S + 3) / 4;
+            const unsigned blocks = (unsigned)((long long)R * m->td.n_rb * n_kg);
+            backward_tile_kernel<<<blocks, 128, EHIC_BT_STAGES * 2048 * sizeof(double), st>>>(m->dm, m->td, ga.xs_cur, m->tw, m->Grow, m->Pbuf, n_kg);
             LAUNCHED();
             CU(cudaGetLastError());
         }

@@ -573,51 +573,100 @@ struct TileDev {
     long long slots;          // n_tiles * 4096: per-replica stride of the tile weights
 };
 
-// Forward, tile form: warp <-> (replica, non-empty 32 x 32 sub-tile, group of QC columns); lane <->
-// row bead.  Column beads are warp-uniform (broadcast LDG.128 of tile-AoS records), the S
-// structures are walked in order with one accumulator per column: no cross-lane reduction and the
-// reference's summation order over the ensemble.  Writes md (data_points order), the Poisson
-// weight of every present slot, and per-block partials of log L.
-template <int KT, int QC>
-__global__ void __launch_bounds__(128)
+// Forward, tile form: CTA <-> (replica, tile of 128 row beads x 32 column beads), 8 warps =
+// 4 row slices x 2 column halves; lane <-> row bead.  Per structure tile (KT structures) the
+// tile-AoS records of the 128 row beads (12 KB, contiguous) and of the 32 column beads (3 KB,
+// contiguous) are staged in shared memory by a 3-stage cp.async ring shared by the whole CTA;
+// column beads are then read with warp-uniform (broadcast) LDS.128.  The S structures are
+// walked in order with one accumulator per column: no cross-lane reduction, the reference's
+// summation order over the ensemble.  Writes md (data_points order), the Poisson weight of
+// every present slot, and per-block partials of log L.
+#define EHIC_FT_STAGES 3
+template <int KT>
+__global__ void __launch_bounds__(256)
 forward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xt, const double *__restrict__ norm,
                     double *__restrict__ md_out, double *__restrict__ tw, double *__restrict__ partA,
                     int want_logl, int nkt)
 {
-    // grid = (blocks per replica, R); 4 warps per block, one item each
+    constexpr int QC = 16;
+    constexpr int REC = KT * 3;                       // doubles per record
+    extern __shared__ __align__(16) double smem[];
+    double *s_dc = smem;                               // [4096]
+    double *s_row = s_dc + 4096;                       // [STAGES][128 * REC]
+    double *s_col = s_row + EHIC_FT_STAGES * 128 * REC;   // [STAGES][32 * REC]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int HALVES = 32 / QC;
-    const int item = blockIdx.x * 4 + warp;
-    const int r = blockIdx.y;
-    double term = 0.0;
-    if (item < HALVES * td.n_sub) {
-        const int h = item % HALVES;
-        const int sub = item / HALVES;
-        const int tile = td.sub_tile[sub], rb = td.sub_rb[sub];
-        const int I = td.tile_I[tile], B = td.tile_B[tile];
-        const int bA = min((4 * I + rb) * 32 + lane, dm.N - 1);
-        const int col0 = 32 * B + h * QC;
-        const unsigned mask = td.mask[((long long)tile * 4 + rb) * 32 + lane] >> (h * QC);
-        const long long pos0 = (((long long)tile * 32 + h * QC) * 4 + rb) * 32 + lane;
-        const double alpha = dm.alpha;
-        const int Np = dm.Np;
-        double acc[QC];
+    const int rb = warp & 3, h = warp >> 2;
+    const int tile = blockIdx.x, r = blockIdx.y;
+    const int I = td.tile_I[tile], B = td.tile_B[tile];
+    const int Np = dm.Np;
+    const int row0 = 128 * I, col0 = 32 * B;           // Np is padded to 32; rows may run past it: clamp the copy
+    const double *recs = xt + (long long)r * nkt * Np * REC;
+    const unsigned mask = td.mask[((long long)tile * 4 + rb) * 32 + lane] >> (h * QC);
+    const bool warp_live = __ballot_sync(0xffffffffu, mask != 0u) != 0u;
+    const double alpha = dm.alpha;
+    const int n_row = min(128, Np - row0);             // row records that exist in xt
+
+    // contact distances of the whole tile: 32 KB, once
+    for (int q = threadIdx.x; q < 2048; q += 256)
+        __pipeline_memcpy_async(&s_dc[q * 2], td.dc + (long long)tile * 4096 + q * 2, 16);
+    auto issue = [&](int kt) {
+        if (kt < nkt) {
+            const int st = kt % EHIC_FT_STAGES;
+            const double *src_row = recs + ((long long)kt * Np + row0) * REC;
+            const double *src_col = recs + ((long long)kt * Np + col0) * REC;
+            for (int q = threadIdx.x; q < n_row * REC / 2; q += 256)
+                __pipeline_memcpy_async(&s_row[st * 128 * REC + q * 2], src_row + q * 2, 16);
+            for (int q = threadIdx.x; q < 32 * REC / 2; q += 256)
+                __pipeline_memcpy_async(&s_col[st * 32 * REC + q * 2], src_col + q * 2, 16);
+        }
+        __pipeline_commit();
+    };
 #pragma unroll
-        for (int q = 0; q < QC; q++) acc[q] = 0.0;
-        const double *recs = xt + (long long)r * nkt * Np * (KT * 3);
-        auto body = [&](int kt, int nvalid) {
-            double own[KT * 3];
-            load_record<KT>(recs + ((long long)kt * Np + bA) * (KT * 3), own);
+    for (int c = 0; c < EHIC_FT_STAGES - 1; c++) issue(c);
+
+    double acc[QC];
+#pragma unroll
+    for (int q = 0; q < QC; q++) acc[q] = 0.0;
+    const int nfull = dm.S / KT;
+    for (int kt = 0; kt < nkt; kt++) {
+        __pipeline_wait_prior(EHIC_FT_STAGES - 2);
+        __syncthreads();
+        issue(kt + EHIC_FT_STAGES - 1);
+        if (!warp_live) continue;
+        const int st = kt % EHIC_FT_STAGES;
+        const int nvalid = kt < nfull ? KT : dm.S - nfull * KT;
+        double own[REC];
+        {
+            const double *p = &s_row[st * 128 * REC + (rb * 32 + lane) * REC];
+#pragma unroll
+            for (int u = 0; u < REC; u++) own[u] = p[u];
+        }
+        const double *pc = &s_col[st * 32 * REC + h * QC * REC];
+        const double *pd = &s_dc[(h * QC * 4 + rb) * 32 + lane];
+        if (nvalid == KT) {
 #pragma unroll
             for (int q = 0; q < QC; q++) {
-                const int oc = min(col0 + q, dm.N - 1);
-                double v[KT * 3];
-                load_record<KT>(recs + ((long long)kt * Np + oc) * (KT * 3), v);
-                const double dc = td.dc[pos0 + q * 128];
+                const double dc = pd[q * 128];
+#pragma unroll
+                for (int t = 0; t < KT; t++) {
+                    double dx = pc[q * REC + 3 * t] - own[3 * t], dy = pc[q * REC + 3 * t + 1] - own[3 * t + 1],
+                           dz = pc[q * REC + 3 * t + 2] - own[3 * t + 2];
+                    double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    double rd = rsqrt_nr(s2);
+                    double tt = alpha * (dc - s2 * rd);
+                    double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                    acc[q] += fma(tt, rq, 1.0);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < QC; q++) {
+                const double dc = pd[q * 128];
 #pragma unroll
                 for (int t = 0; t < KT; t++) {
                     if (t < nvalid) {
-                        double dx = v[3 * t] - own[3 * t], dy = v[3 * t + 1] - own[3 * t + 1], dz = v[3 * t + 2] - own[3 * t + 2];
+                        double dx = pc[q * REC + 3 * t] - own[3 * t], dy = pc[q * REC + 3 * t + 1] - own[3 * t + 1],
+                               dz = pc[q * REC + 3 * t + 2] - own[3 * t + 2];
                         double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
                         double rd = rsqrt_nr(s2);
                         double tt = alpha * (dc - s2 * rd);
@@ -626,32 +675,34 @@ forward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xt, cons
                     }
                 }
             }
-        };
-        const int nfull = dm.S / KT;
-        for (int kt = 0; kt < nfull; kt++) body(kt, KT);
-        if (nfull < nkt) body(nfull, dm.S - nfull * KT);
-        const double nrm = norm[r];
+        }
+    }
+    __pipeline_wait_prior(0);
+
+    double term = 0.0;
+    const double nrm = norm[r];
+    const long long pos0 = (((long long)tile * 32 + h * QC) * 4 + rb) * 32 + lane;
 #pragma unroll
-        for (int q = 0; q < QC; q++) {
-            if ((mask >> q) & 1u) {
-                const long long pos = pos0 + q * 128;
-                const double md = acc[q] * (0.5 * nrm);
-                const double c = td.cnt[pos];
-                if (md_out) md_out[(long long)r * dm.M + td.orig[pos]] = md;
-                if (tw) {
-                    double em = __dsub_rn(1.0, __ddiv_rn(c, md));
-                    tw[(long long)r * td.slots + pos] = __dmul_rn(__dmul_rn(__dmul_rn(0.5, em), nrm), alpha);
-                }
-                if (want_logl) term += c * log(md) - md;
+    for (int q = 0; q < QC; q++) {
+        if ((mask >> q) & 1u) {
+            const long long pos = pos0 + q * 128;
+            const double md = acc[q] * (0.5 * nrm);
+            const double c = td.cnt[pos];
+            if (md_out) md_out[(long long)r * dm.M + td.orig[pos]] = md;
+            if (tw) {
+                double em = __dsub_rn(1.0, __ddiv_rn(c, md));
+                tw[(long long)r * td.slots + pos] = __dmul_rn(__dmul_rn(__dmul_rn(0.5, em), nrm), alpha);
             }
+            if (want_logl) term += c * log(md) - md;
         }
     }
     if (want_logl) {
-        __shared__ double sh[4];
+        __shared__ double sh[8];
         double v = warp_sum(term);
         if (lane == 0) sh[warp] = v;
         __syncthreads();
-        if (threadIdx.x == 0) partA[(long long)r * gridDim.x + blockIdx.x] = (sh[0] + sh[1]) + (sh[2] + sh[3]);
+        if (threadIdx.x == 0)
+            partA[(long long)r * gridDim.x + blockIdx.x] = ((sh[0] + sh[1]) + (sh[2] + sh[3])) + ((sh[4] + sh[5]) + (sh[6] + sh[7]));
     }
 }
 
@@ -681,74 +732,107 @@ __device__ __forceinline__ void reduce8(double (&r)[8], int lane)
     r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
 }
 
-// Backward, tile form: warp <-> (replica, structure, row block of 128 beads); each lane owns 4 row
-// beads (accumulated in registers over all column slices of the row block) and, per group of 8
-// warp-uniform column beads, the partial reactions, which are summed over the warp with reduce8
-// and written to the per-row-block partial buffer P[r][k][I][bead][3].  No atomics.
+// Backward, tile form: CTA <-> (replica, row block of 128 beads, group of 4 structures); warp <->
+// structure; each lane owns 4 row beads (accumulated in registers over all column slices of the row
+// block).  The (contact distance, weight) slots do not depend on the structure: chunks of 8 columns
+// (1024 slots, 16 KB) stream once per CTA through a 3-stage cp.async ring shared by the 4 warps.
+// Column beads live one per lane and are broadcast with shuffles; their partial reactions are
+// summed over the warp with reduce8 and written to the per-row-block buffer P[r][k][I][bead][3].
+// No atomics: action and reaction of every pair are evaluated ONCE.
+#define EHIC_BT_STAGES 3
 __global__ void __launch_bounds__(128)
 backward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xs, const double *__restrict__ tw,
-                     double *__restrict__ Grow, double *__restrict__ P, long long n_items)
+                     double *__restrict__ Grow, double *__restrict__ P, int n_kg)
 {
-    const int lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (item >= n_items) return;
-    const int I = (int)(item % td.n_rb);
-    const long long rk = item / td.n_rb;            // r * S + k
-    const int r = (int)(rk / dm.S);
+    extern __shared__ __align__(16) double smem[];        // [STAGES][2][1024]: dc, w
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kg = blockIdx.x % n_kg;
+    const int I = (blockIdx.x / n_kg) % td.n_rb;
+    const int r = blockIdx.x / (n_kg * td.n_rb);
+    const int k = kg * 4 + warp;
+    const bool k_ok = k < dm.S;
+    const long long rk = (long long)r * dm.S + (k_ok ? k : dm.S - 1);
     const int Np = dm.Np;
     const double *xk = xs + rk * 3LL * Np;
     const double alpha = dm.alpha;
-    int bA[4];
     double xb[4][3], acc[4][3];
 #pragma unroll
     for (int rb = 0; rb < 4; rb++) {
-        bA[rb] = min((4 * I + rb) * 32 + lane, dm.N - 1);
-        xb[rb][0] = xk[bA[rb]]; xb[rb][1] = xk[Np + bA[rb]]; xb[rb][2] = xk[2 * Np + bA[rb]];
+        const int b = min((4 * I + rb) * 32 + lane, dm.N - 1);
+        xb[rb][0] = xk[b]; xb[rb][1] = xk[Np + b]; xb[rb][2] = xk[2 * Np + b];
         acc[rb][0] = acc[rb][1] = acc[rb][2] = 0.0;
     }
     const double *twr = tw + (long long)r * td.slots;
     double *Pk = P + (rk * td.n_rb + I) * (long long)dm.N * 3;
-    for (int t = td.rb_begin[I]; t < td.rb_begin[I + 1]; t++) {
-        const int col0 = 32 * td.tile_B[t];
-        unsigned m[4];
-#pragma unroll
-        for (int rb = 0; rb < 4; rb++) m[rb] = td.mask[((long long)t * 4 + rb) * 32 + lane];
-        const long long tbase = (long long)t * 4096 + lane;
-        for (int qg = 0; qg < 4; qg++) {
-            double rx[8], ry[8], rz[8];
-#pragma unroll
-            for (int qq = 0; qq < 8; qq++) {
-                const int q = qg * 8 + qq;
-                const int oc = min(col0 + q, dm.N - 1);
-                const double ox = xk[oc], oy = xk[Np + oc], oz = xk[2 * Np + oc];
-                double fx = 0.0, fy = 0.0, fz = 0.0;
-#pragma unroll
-                for (int rb = 0; rb < 4; rb++) {
-                    const long long pos = tbase + (q * 4 + rb) * 32;
-                    const double dc = td.dc[pos], w = twr[pos];
-                    double dx = ox - xb[rb][0], dy = oy - xb[rb][1], dz = oz - xb[rb][2];
-                    double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    double rd = rsqrt_nr(s2);
-                    double tt = alpha * (dc - s2 * rd);
-                    double rq = rsqrt_nr(fma(tt, tt, 1.0));
-                    double f = w * ((rq * rq) * (rq * rd));
-                    f = ((m[rb] >> q) & 1u) ? f : 0.0;
-                    acc[rb][0] = fma(f, dx, acc[rb][0]); acc[rb][1] = fma(f, dy, acc[rb][1]); acc[rb][2] = fma(f, dz, acc[rb][2]);
-                    fx = fma(-f, dx, fx); fy = fma(-f, dy, fy); fz = fma(-f, dz, fz);
-                }
-                rx[qq] = fx; ry[qq] = fy; rz[qq] = fz;
-            }
-            reduce8(rx, lane); reduce8(ry, lane); reduce8(rz, lane);
-            if ((lane & 3) == 0) {
-                const int col = col0 + qg * 8 + (((lane >> 2) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 4) & 1));
-                if (col < dm.N) { double *o = Pk + (long long)col * 3; o[0] = rx[0]; o[1] = ry[0]; o[2] = rz[0]; }
+    const int t0 = td.rb_begin[I], n_tiles = td.rb_begin[I + 1] - t0;
+    const int n_chunks = n_tiles * 4;
+    auto issue = [&](int c) {
+        if (c < n_chunks) {
+            const int st = c % EHIC_BT_STAGES;
+            const long long base = (long long)(t0 + (c >> 2)) * 4096 + (c & 3) * 1024;
+            double *d0 = smem + st * 2048;
+            for (int q = threadIdx.x; q < 512; q += 128) {
+                __pipeline_memcpy_async(&d0[q * 2], td.dc + base + q * 2, 16);
+                __pipeline_memcpy_async(&d0[1024 + q * 2], twr + base + q * 2, 16);
             }
         }
-    }
+        __pipeline_commit();
+    };
 #pragma unroll
-    for (int rb = 0; rb < 4; rb++) {
-        const int b = (4 * I + rb) * 32 + lane;
-        if (b < dm.N) { double *o = Grow + (rk * dm.N + b) * 3; o[0] = acc[rb][0]; o[1] = acc[rb][1]; o[2] = acc[rb][2]; }
+    for (int c = 0; c < EHIC_BT_STAGES - 1; c++) issue(c);
+
+    double cx = 0.0, cy = 0.0, cz = 0.0;
+    unsigned m[4] = {0u, 0u, 0u, 0u};
+    int col0 = 0;
+    for (int c = 0; c < n_chunks; c++) {
+        __pipeline_wait_prior(EHIC_BT_STAGES - 2);
+        __syncthreads();
+        issue(c + EHIC_BT_STAGES - 1);
+        const int qg = c & 3;
+        if (qg == 0) {                                   // new tile: column beads (one per lane) and masks
+            const int t = t0 + (c >> 2);
+            col0 = 32 * td.tile_B[t];
+            const int oc = min(col0 + lane, dm.N - 1);
+            cx = xk[oc]; cy = xk[Np + oc]; cz = xk[2 * Np + oc];
+#pragma unroll
+            for (int rb = 0; rb < 4; rb++) m[rb] = td.mask[((long long)t * 4 + rb) * 32 + lane];
+        }
+        const double *sd = smem + (c % EHIC_BT_STAGES) * 2048 + lane;
+        double rx[8], ry[8], rz[8];
+#pragma unroll
+        for (int qq = 0; qq < 8; qq++) {
+            const int q = qg * 8 + qq;
+            const double ox = __shfl_sync(0xffffffffu, cx, q), oy = __shfl_sync(0xffffffffu, cy, q),
+                         oz = __shfl_sync(0xffffffffu, cz, q);
+            double fx = 0.0, fy = 0.0, fz = 0.0;
+#pragma unroll
+            for (int rb = 0; rb < 4; rb++) {
+                const double dc = sd[(qq * 4 + rb) * 32], w = sd[1024 + (qq * 4 + rb) * 32];
+                double dx = ox - xb[rb][0], dy = oy - xb[rb][1], dz = oz - xb[rb][2];
+                double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                double rd = rsqrt_nr(s2);
+                double tt = alpha * (dc - s2 * rd);
+                double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                double f = w * ((rq * rq) * (rq * rd));
+                f = ((m[rb] >> q) & 1u) ? f : 0.0;
+                acc[rb][0] = fma(f, dx, acc[rb][0]); acc[rb][1] = fma(f, dy, acc[rb][1]); acc[rb][2] = fma(f, dz, acc[rb][2]);
+                fx = fma(-f, dx, fx); fy = fma(-f, dy, fy); fz = fma(-f, dz, fz);
+            }
+            rx[qq] = fx; ry[qq] = fy; rz[qq] = fz;
+        }
+        reduce8(rx, lane); reduce8(ry, lane); reduce8(rz, lane);
+        if ((lane & 3) == 0 && k_ok) {
+            const int col = col0 + qg * 8 + (((lane >> 2) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 4) & 1));
+            if (col < dm.N) { double *o = Pk + (long long)col * 3; o[0] = rx[0]; o[1] = ry[0]; o[2] = rz[0]; }
+        }
+    }
+    __pipeline_wait_prior(0);
+    if (k_ok) {
+#pragma unroll
+        for (int rb = 0; rb < 4; rb++) {
+            const int b = (4 * I + rb) * 32 + lane;
+            if (b < dm.N) { double *o = Grow + (rk * dm.N + b) * 3; o[0] = acc[rb][0]; o[1] = acc[rb][1]; o[2] = acc[rb][2]; }
+        }
     }
 }
 
