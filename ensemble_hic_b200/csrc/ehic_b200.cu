@@ -49,6 +49,8 @@ struct ehic_model {
     DevModel dm{};
     ContactLayout layout;           // host copy (sizes, perm)
     bool use_tiles = false;         // dense list + fast mode: symmetric tile path
+    bool nb_fused = false;          // tiles cover all bead pairs: nonbonded force rides in the backward tile kernel
+    const unsigned char *tile_clean = nullptr;
     TileDev td{};
     double tile_fill = 0.0;
     int nA_tile = 0, nKc = 0;       // forward-tile blocks per replica; combine blocks per structure
@@ -255,6 +257,8 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         UPT(TL.sub_tile, sub_tile); UPT(TL.sub_rb, sub_rb); UPT(TL.exists, exists);
         UPT(TL.mask, mask); UPT(TL.dc, dc); UPT(TL.cnt, cnt); UPT(orig, orig);
 #undef UPT
+        rc = upload(m, TL.clean, &m->tile_clean); if (rc) { ehic_model_destroy(m); return rc; }
+        { const char *nf = getenv("EHIC_NB_FUSED"); m->nb_fused = TL.covers_all_pairs && !(nf && !strcmp(nf, "0")); }
     }
     // free the big host vectors we no longer need
     std::vector<int32_t>().swap(L.ent_j); std::vector<double>().swap(L.ent_dc);
@@ -295,8 +299,11 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
             ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed");
         }
         // both tile kernels use more than the 48 KB of static shared memory
-        cudaError_t e1 = cudaFuncSetAttribute(backward_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e1 = cudaFuncSetAttribute(backward_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)(EHIC_BT_STAGES * 2048 * sizeof(double)));
+        if (e1 == cudaSuccess)
+            e1 = cudaFuncSetAttribute(backward_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(EHIC_BT_STAGES * 2048 * sizeof(double)));
         cudaError_t e2 = cudaSuccess;
         const int fsm = (int)forward_tile_smem(m->kt);
         switch (m->kt) {
@@ -394,7 +401,7 @@ static int launch_pack(ehic_model *m, int R, const double *d_x, double *xs, doub
 }
 
 static int launch_forward(ehic_model *m, int R, const double *xs, const double *d_norm, double *d_md,
-                          bool want_w, bool want_logl, cudaStream_t st)
+                          bool want_w, bool want_logl, cudaStream_t st, const double *d_lammda = nullptr)
 {
     if (m->dm.M == 0) {
         if (want_logl) CU(cudaMemsetAsync(m->partA, 0, sizeof(double) * (size_t)R * std::max(m->nA, 1), st));
@@ -406,9 +413,9 @@ static int launch_forward(ehic_model *m, int R, const double *xs, const double *
         double *twp = want_w ? m->tw : nullptr;
         const size_t sm = forward_tile_smem(m->kt);
         switch (m->kt) {
-        case 4: forward_tile_kernel<4><<<gridt, 256, sm, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_md, twp, m->partA, want_logl, m->nkt); break;
-        case 2: forward_tile_kernel<2><<<gridt, 256, sm, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_md, twp, m->partA, want_logl, m->nkt); break;
-        default: forward_tile_kernel<1><<<gridt, 256, sm, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_md, twp, m->partA, want_logl, m->nkt); break;
+        case 4: forward_tile_kernel<4><<<gridt, 256, sm, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_lammda, d_md, twp, m->partA, want_logl, m->nkt); break;
+        case 2: forward_tile_kernel<2><<<gridt, 256, sm, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_lammda, d_md, twp, m->partA, want_logl, m->nkt); break;
+        default: forward_tile_kernel<1><<<gridt, 256, sm, st>>>(m->dm, m->td, m->xt[m->cur_xt], d_norm, d_lammda, d_md, twp, m->partA, want_logl, m->nkt); break;
         }
         LAUNCHED();
         CU(cudaGetLastError());
@@ -457,9 +464,13 @@ static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_
     if (m->use_tiles) {
         if (ga.contact) {
             KernelTimer kt_(m, KC_GATHER, st);
-            const int n_kg = (m->dm.S + 3) / 4;
-            const unsigned blocks = (unsigned)((long long)R * m->td.n_rb * n_kg);
-            backward_tile_kernel<<<blocks, 128, EHIC_BT_STAGES * 2048 * sizeof(double), st>>>(m->dm, m->td, ga.xs_cur, m->tw, m->Grow, m->Pbuf, n_kg);
+            BackwardTileArgs ba{};
+            ba.xs = ga.xs_cur; ba.tw = m->tw; ba.beta = ga.beta; ba.Grow = m->Grow; ba.P = m->Pbuf;
+            ba.tile_clean = m->tile_clean; ba.n_kg = (m->dm.S + 3) / 4; ba.nb = ga.nb_fused; ba.r_max = m->r_max;
+            const unsigned blocks = (unsigned)((long long)R * m->td.n_rb * ba.n_kg);
+            const size_t sm = EHIC_BT_STAGES * 2048 * sizeof(double);
+            if (ga.nb_fused) backward_tile_kernel<true><<<blocks, 128, sm, st>>>(m->dm, m->td, ba);
+            else backward_tile_kernel<false><<<blocks, 128, sm, st>>>(m->dm, m->td, ba);
             LAUNCHED();
             CU(cudaGetLastError());
         }
@@ -525,12 +536,15 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     m->cur_xt = 0;
     const bool need_forward = (lik && (d_grad || d_energies)) || d_md;
     if (need_forward) {
-        rc = launch_forward(m, R, m->xs[0], d_norm, d_md, lik && d_grad, lik && d_energies, st);
+        rc = launch_forward(m, R, m->xs[0], d_norm, d_md, lik && d_grad, lik && d_energies, st, d_lammda);
         if (rc) return rc;
     }
-    const bool need_prior = prior_terms && (d_grad || d_energies);
+    // pure gradient calls on the tile path evaluate the nonbonded force inside the backward tile kernel
+    const bool fuse_nb = m->use_tiles && m->nb_fused && lik && (terms & EHIC_TERM_NONBONDED) && d_grad && !d_energies;
+    const int kernel_prior_terms = fuse_nb ? (prior_terms & ~EHIC_TERM_NONBONDED) : prior_terms;
+    const bool need_prior = kernel_prior_terms && (d_grad || d_energies);
     if (need_prior) {
-        rc = launch_prior(m, R, prior_terms, m->xs[0], d_beta, d_grad != nullptr, d_energies != nullptr, st);
+        rc = launch_prior(m, R, kernel_prior_terms, m->xs[0], d_beta, d_grad != nullptr, d_energies != nullptr, st);
         if (rc) return rc;
     }
     if (d_grad) {
@@ -538,6 +552,7 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
         ga.xt = m->xt[0]; ga.xs_cur = m->xs[0]; ga.wbuf = m->wbuf; ga.lammda = d_lammda;
         ga.gprior = need_prior ? m->gprior : nullptr;
         ga.grad = d_grad; ga.contact = lik ? 1 : 0;
+        ga.nb_fused = fuse_nb ? 1 : 0; ga.beta = d_beta;
         rc = launch_gather(m, ga, R, st);
         if (rc) return rc;
     }
@@ -566,12 +581,17 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
         const bool first = (s == 0), last = (s == n_steps);
         const bool ends = first || last;
         m->cur_xt = cur;
-        rc = launch_forward(m, R, m->xs[cur], d_norm, nullptr, true, ends, st);
+        rc = launch_forward(m, R, m->xs[cur], d_norm, nullptr, true, ends, st, d_lammda);
         if (rc) return rc;
-        rc = launch_prior(m, R, prior_terms, m->xs[cur], d_beta, true, ends, st);
-        if (rc) return rc;
+        const bool fuse_nb = m->use_tiles && m->nb_fused && !ends;
+        const int kpt = fuse_nb ? (prior_terms & ~EHIC_TERM_NONBONDED) : prior_terms;
+        if (kpt) {
+            rc = launch_prior(m, R, kpt, m->xs[cur], d_beta, true, ends, st);
+            if (rc) return rc;
+        }
         GatherArgs ga{};
-        ga.xt = m->xt[cur]; ga.xs_cur = m->xs[cur]; ga.wbuf = m->wbuf; ga.lammda = d_lammda; ga.gprior = m->gprior;
+        ga.xt = m->xt[cur]; ga.xs_cur = m->xs[cur]; ga.wbuf = m->wbuf; ga.lammda = d_lammda; ga.gprior = kpt ? m->gprior : nullptr;
+        ga.nb_fused = fuse_nb ? 1 : 0; ga.beta = d_beta;
         ga.grad = nullptr; ga.partK = ends ? m->partK : nullptr; ga.contact = 1;
         ga.p = d_p; ga.eps = d_eps; ga.kick = ends ? 0.5 : 1.0;
         ga.xs_next = last ? nullptr : m->xs[cur ^ 1];

@@ -407,6 +407,8 @@ struct GatherArgs {
     double *grad;           // [R][S][N][3] or NULL
     double *partK;          // [items] kinetic partials or NULL
     int contact;            // evaluate the contact term
+    int nb_fused;           // tile path: nonbonded force evaluated inside backward_tile_kernel
+    const double *beta;     // [R] or NULL (only read when nb_fused)
     // leapfrog epilogue (all NULL/0 outside HMC)
     double *p;              // [R][S][N][3] momenta, updated in place:  p -= kick * eps * g
     const double *eps;      // [R]
@@ -581,12 +583,12 @@ struct TileDev {
 // walked in order with one accumulator per column: no cross-lane reduction, the reference's
 // summation order over the ensemble.  Writes md (data_points order), the Poisson weight of
 // every present slot, and per-block partials of log L.
-#define EHIC_FT_STAGES 3
+#define EHIC_FT_STAGES 2
 template <int KT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 forward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xt, const double *__restrict__ norm,
-                    double *__restrict__ md_out, double *__restrict__ tw, double *__restrict__ partA,
-                    int want_logl, int nkt)
+                    const double *__restrict__ lammda, double *__restrict__ md_out, double *__restrict__ tw,
+                    double *__restrict__ partA, int want_logl, int nkt)
 {
     constexpr int QC = 16;
     constexpr int REC = KT * 3;                       // doubles per record
@@ -681,6 +683,7 @@ forward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xt, cons
 
     double term = 0.0;
     const double nrm = norm[r];
+    const double lam = lammda ? lammda[r] : 1.0;       // the backward tile kernel consumes lammda * w
     const long long pos0 = (((long long)tile * 32 + h * QC) * 4 + rb) * 32 + lane;
 #pragma unroll
     for (int q = 0; q < QC; q++) {
@@ -691,7 +694,7 @@ forward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xt, cons
             if (md_out) md_out[(long long)r * dm.M + td.orig[pos]] = md;
             if (tw) {
                 double em = __dsub_rn(1.0, __ddiv_rn(c, md));
-                tw[(long long)r * td.slots + pos] = __dmul_rn(__dmul_rn(__dmul_rn(0.5, em), nrm), alpha);
+                tw[(long long)r * td.slots + pos] = lam * __dmul_rn(__dmul_rn(__dmul_rn(0.5, em), nrm), alpha);
             }
             if (want_logl) term += c * log(md) - md;
         }
@@ -739,31 +742,107 @@ __device__ __forceinline__ void reduce8(double (&r)[8], int lane)
 // Column beads live one per lane and are broadcast with shuffles; their partial reactions are
 // summed over the warp with reduce8 and written to the per-row-block buffer P[r][k][I][bead][3].
 // No atomics: action and reaction of every pair are evaluated ONCE.
+//
+// The weights arrive already multiplied by lammda.  When the tiles cover every bead pair (NB),
+// the repulsive nonbonded force is fused in: the pair distance is already there, the contact test
+// is one compare against a per-row-bead coarse bound, and the rare hits are handled in a
+// warp-uniform branch (beta * 2 k (r_b + r_o - d)^3 / d, forcefield_c.pyx:51-57).
+// "Clean" tiles (strictly above the diagonal blocks, every slot present, no clamped beads) skip
+// all masking.
 #define EHIC_BT_STAGES 3
-__global__ void __launch_bounds__(128)
-backward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xs, const double *__restrict__ tw,
-                     double *__restrict__ Grow, double *__restrict__ P, int n_kg)
+
+struct BackwardTileArgs {
+    const double *xs, *tw, *beta;
+    double *Grow, *P;
+    const unsigned char *tile_clean;   // [n_tiles]
+    int n_kg, nb;                      // structure groups per row block; fuse the nonbonded term
+    double r_max;
+};
+
+template <bool MASKED, bool NB>
+__device__ __forceinline__ void backward_chunk(const DevModel &dm, const double *__restrict__ sd, int qg, int lane,
+                                               double cx, double cy, double cz, double cr, const unsigned (&m)[4],
+                                               const int (&brow)[4], int col0, const double (&xb)[4][3],
+                                               const double (&rr)[4], const double (&coarse)[4], double nbs,
+                                               double (&acc)[4][3], double (&rx)[8], double (&ry)[8], double (&rz)[8])
+{
+    const double alpha = dm.alpha;
+#pragma unroll
+    for (int qq = 0; qq < 8; qq++) {
+        const int q = qg * 8 + qq;
+        const double ox = __shfl_sync(0xffffffffu, cx, q), oy = __shfl_sync(0xffffffffu, cy, q),
+                     oz = __shfl_sync(0xffffffffu, cz, q);
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        unsigned hits = 0u;
+#pragma unroll
+        for (int rb = 0; rb < 4; rb++) {
+            const double dc = sd[(qq * 4 + rb) * 32], w = sd[1024 + (qq * 4 + rb) * 32];
+            double dx = ox - xb[rb][0], dy = oy - xb[rb][1], dz = oz - xb[rb][2];
+            double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            double rd = rsqrt_nr(s2);
+            double tt = alpha * (dc - s2 * rd);
+            double rq = rsqrt_nr(fma(tt, tt, 1.0));
+            double f = w * ((rq * rq) * (rq * rd));
+            if (MASKED) f = ((m[rb] >> q) & 1u) ? f : 0.0;
+            acc[rb][0] = fma(f, dx, acc[rb][0]); acc[rb][1] = fma(f, dy, acc[rb][1]); acc[rb][2] = fma(f, dz, acc[rb][2]);
+            fx = fma(-f, dx, fx); fy = fma(-f, dy, fy); fz = fma(-f, dz, fz);
+            if (NB) {
+                bool h = s2 < coarse[rb];
+                if (MASKED) h = h && (col0 + q > brow[rb]) && (col0 + q < dm.N) && (brow[rb] >= 0);
+                hits |= h ? (1u << rb) : 0u;
+            }
+        }
+        if (NB && __any_sync(0xffffffffu, hits != 0u)) {
+            // rare: some pair of this column is within the coarse contact range; redo those rows
+            const double ro = __shfl_sync(0xffffffffu, cr, q);
+#pragma unroll
+            for (int rb = 0; rb < 4; rb++) {
+                if (!__any_sync(0xffffffffu, (hits >> rb) & 1u)) continue;
+                double dx = ox - xb[rb][0], dy = oy - xb[rb][1], dz = oz - xb[rb][2];
+                double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                const double d0 = rr[rb] + ro;
+                if (((hits >> rb) & 1u) && s2 < d0 * d0) {
+                    const double rd = rsqrt_nr(s2);
+                    const double a = d0 - s2 * rd;
+                    const double g = nbs * ((a * a) * (a * rd));
+                    acc[rb][0] = fma(g, dx, acc[rb][0]); acc[rb][1] = fma(g, dy, acc[rb][1]); acc[rb][2] = fma(g, dz, acc[rb][2]);
+                    fx = fma(-g, dx, fx); fy = fma(-g, dy, fy); fz = fma(-g, dz, fz);
+                }
+            }
+        }
+        rx[qq] = fx; ry[qq] = fy; rz[qq] = fz;
+    }
+}
+
+template <bool NB>
+__global__ void __launch_bounds__(128, 3)
+backward_tile_kernel(DevModel dm, TileDev td, BackwardTileArgs ba)
 {
     extern __shared__ __align__(16) double smem[];        // [STAGES][2][1024]: dc, w
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int kg = blockIdx.x % n_kg;
-    const int I = (blockIdx.x / n_kg) % td.n_rb;
-    const int r = blockIdx.x / (n_kg * td.n_rb);
+    const int kg = blockIdx.x % ba.n_kg;
+    const int I = (blockIdx.x / ba.n_kg) % td.n_rb;
+    const int r = blockIdx.x / (ba.n_kg * td.n_rb);
     const int k = kg * 4 + warp;
     const bool k_ok = k < dm.S;
     const long long rk = (long long)r * dm.S + (k_ok ? k : dm.S - 1);
     const int Np = dm.Np;
-    const double *xk = xs + rk * 3LL * Np;
-    const double alpha = dm.alpha;
-    double xb[4][3], acc[4][3];
+    const double *xk = ba.xs + rk * 3LL * Np;
+    int brow[4];
+    double xb[4][3], acc[4][3], rr[4], coarse[4];
 #pragma unroll
     for (int rb = 0; rb < 4; rb++) {
-        const int b = min((4 * I + rb) * 32 + lane, dm.N - 1);
+        const int b0 = (4 * I + rb) * 32 + lane;
+        brow[rb] = b0 < dm.N ? b0 : -1;                   // -1: no such bead (loads use bead 0)
+        const int b = b0 < dm.N ? b0 : 0;
         xb[rb][0] = xk[b]; xb[rb][1] = xk[Np + b]; xb[rb][2] = xk[2 * Np + b];
         acc[rb][0] = acc[rb][1] = acc[rb][2] = 0.0;
+        rr[rb] = dm.radii[b];
+        coarse[rb] = (rr[rb] + ba.r_max) * (rr[rb] + ba.r_max);
     }
-    const double *twr = tw + (long long)r * td.slots;
-    double *Pk = P + (rk * td.n_rb + I) * (long long)dm.N * 3;
+    const double nbs = NB ? (ba.beta ? ba.beta[r] : 1.0) * 2.0 * dm.k_nb : 0.0;
+    const double *twr = ba.tw + (long long)r * td.slots;
+    double *Pk = ba.P + (rk * td.n_rb + I) * (long long)dm.N * 3;
     const int t0 = td.rb_begin[I], n_tiles = td.rb_begin[I + 1] - t0;
     const int n_chunks = n_tiles * 4;
     auto issue = [&](int c) {
@@ -781,9 +860,10 @@ backward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xs, con
 #pragma unroll
     for (int c = 0; c < EHIC_BT_STAGES - 1; c++) issue(c);
 
-    double cx = 0.0, cy = 0.0, cz = 0.0;
+    double cx = 0.0, cy = 0.0, cz = 0.0, cr = 0.0;
     unsigned m[4] = {0u, 0u, 0u, 0u};
     int col0 = 0;
+    bool clean = false;
     for (int c = 0; c < n_chunks; c++) {
         __pipeline_wait_prior(EHIC_BT_STAGES - 2);
         __syncthreads();
@@ -794,32 +874,17 @@ backward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xs, con
             col0 = 32 * td.tile_B[t];
             const int oc = min(col0 + lane, dm.N - 1);
             cx = xk[oc]; cy = xk[Np + oc]; cz = xk[2 * Np + oc];
+            if (NB) cr = dm.radii[oc];
+            clean = ba.tile_clean[t] != 0;
+            if (!clean) {
 #pragma unroll
-            for (int rb = 0; rb < 4; rb++) m[rb] = td.mask[((long long)t * 4 + rb) * 32 + lane];
+                for (int rb = 0; rb < 4; rb++) m[rb] = td.mask[((long long)t * 4 + rb) * 32 + lane];
+            }
         }
         const double *sd = smem + (c % EHIC_BT_STAGES) * 2048 + lane;
         double rx[8], ry[8], rz[8];
-#pragma unroll
-        for (int qq = 0; qq < 8; qq++) {
-            const int q = qg * 8 + qq;
-            const double ox = __shfl_sync(0xffffffffu, cx, q), oy = __shfl_sync(0xffffffffu, cy, q),
-                         oz = __shfl_sync(0xffffffffu, cz, q);
-            double fx = 0.0, fy = 0.0, fz = 0.0;
-#pragma unroll
-            for (int rb = 0; rb < 4; rb++) {
-                const double dc = sd[(qq * 4 + rb) * 32], w = sd[1024 + (qq * 4 + rb) * 32];
-                double dx = ox - xb[rb][0], dy = oy - xb[rb][1], dz = oz - xb[rb][2];
-                double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                double rd = rsqrt_nr(s2);
-                double tt = alpha * (dc - s2 * rd);
-                double rq = rsqrt_nr(fma(tt, tt, 1.0));
-                double f = w * ((rq * rq) * (rq * rd));
-                f = ((m[rb] >> q) & 1u) ? f : 0.0;
-                acc[rb][0] = fma(f, dx, acc[rb][0]); acc[rb][1] = fma(f, dy, acc[rb][1]); acc[rb][2] = fma(f, dz, acc[rb][2]);
-                fx = fma(-f, dx, fx); fy = fma(-f, dy, fy); fz = fma(-f, dz, fz);
-            }
-            rx[qq] = fx; ry[qq] = fy; rz[qq] = fz;
-        }
+        if (clean) backward_chunk<false, NB>(dm, sd, qg, lane, cx, cy, cz, cr, m, brow, col0, xb, rr, coarse, nbs, acc, rx, ry, rz);
+        else backward_chunk<true, NB>(dm, sd, qg, lane, cx, cy, cz, cr, m, brow, col0, xb, rr, coarse, nbs, acc, rx, ry, rz);
         reduce8(rx, lane); reduce8(ry, lane); reduce8(rz, lane);
         if ((lane & 3) == 0 && k_ok) {
             const int col = col0 + qg * 8 + (((lane >> 2) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 4) & 1));
@@ -830,14 +895,13 @@ backward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xs, con
     if (k_ok) {
 #pragma unroll
         for (int rb = 0; rb < 4; rb++) {
-            const int b = (4 * I + rb) * 32 + lane;
-            if (b < dm.N) { double *o = Grow + (rk * dm.N + b) * 3; o[0] = acc[rb][0]; o[1] = acc[rb][1]; o[2] = acc[rb][2]; }
+            if (brow[rb] >= 0) { double *o = ba.Grow + (rk * dm.N + brow[rb]) * 3; o[0] = acc[rb][0]; o[1] = acc[rb][1]; o[2] = acc[rb][2]; }
         }
     }
 }
 
 // Combine + epilogue of the tile path: thread <-> (replica, structure, bead).
-// g = lammda * (row sum + sum over row blocks of the reaction partials, ascending) + gprior,
+// g = (row sum + sum over row blocks of the reaction partials, ascending) + gprior,
 // then the same leapfrog epilogue as gather_kernel.
 __global__ void __launch_bounds__(256)
 combine_kernel(DevModel dm, TileDev td, GatherArgs ga, const double *__restrict__ Grow, const double *__restrict__ P,
@@ -860,8 +924,7 @@ combine_kernel(DevModel dm, TileDev td, GatherArgs ga, const double *__restrict_
                 }
             }
         }
-        const double lam = ga.lammda ? ga.lammda[r] : 1.0;
-        g0 *= lam; g1 *= lam; g2 *= lam;
+        // lammda (and beta for the fused nonbonded force) are already inside the tile sums
         if (ga.gprior) { g0 += ga.gprior[at]; g1 += ga.gprior[at + 1]; g2 += ga.gprior[at + 2]; }
         if (ga.grad) { ga.grad[at] = g0; ga.grad[at + 1] = g1; ga.grad[at + 2] = g2; }
         if (ga.p) {

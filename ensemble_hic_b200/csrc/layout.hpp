@@ -63,6 +63,8 @@ struct TileLayout {
     std::vector<double> dc, cnt;              // [n_tiles*4096]
     std::vector<int64_t> orig;                // [n_tiles*4096] row of data_points, -1 = absent
     std::vector<int32_t> exists;              // [n_rb][n_slices]: tile index or -1
+    std::vector<unsigned char> clean;         // [n_tiles]: above the diagonal blocks, all slots present, no clamped beads
+    bool covers_all_pairs = false;            // every tile (I, B >= 4 I) exists: the nonbonded force can ride along
     double fill = 0.0;
 };
 
@@ -112,6 +114,17 @@ inline void build_tiles(const ContactLayout &L, const int64_t *data, const doubl
             if (any) { T.sub_tile.push_back(t); T.sub_rb.push_back(rb); }
         }
     T.exists = id;
+    T.clean.assign(T.n_tiles, 0);
+    for (int32_t t = 0; t < T.n_tiles; t++) {
+        const int32_t I = T.tile_I[t], B = T.tile_B[t];
+        bool ok = B >= 4 * I + 4 && 32 * B + 31 < N && (4 * I + 3) * 32 + 31 < N;
+        for (int32_t q = 0; ok && q < 128; q++) ok = T.mask[(size_t)t * 128 + q] == 0xffffffffu;
+        T.clean[t] = ok ? 1 : 0;
+    }
+    T.covers_all_pairs = true;
+    for (int32_t I = 0; I < T.n_rb; I++)
+        for (int32_t B = 4 * I; B < n_sl; B++)
+            if (id[(size_t)I * n_sl + B] < 0) T.covers_all_pairs = false;
     T.eligible = true;
 }
 
