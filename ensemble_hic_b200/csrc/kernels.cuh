@@ -762,18 +762,19 @@ struct BackwardTileArgs {
 template <bool MASKED, bool NB>
 __device__ __forceinline__ void backward_chunk(const DevModel &dm, const double *__restrict__ sd, int qg, int lane,
                                                double cx, double cy, double cz, double cr, const unsigned (&m)[4],
-                                               const int (&brow)[4], int col0, const double (&xb)[4][3],
-                                               const double (&rr)[4], const double (&coarse)[4], double nbs,
+                                               int row0, int col0, const double (&xb)[4][3],
+                                               double coarse, double nbs,
                                                double (&acc)[4][3], double (&rx)[8], double (&ry)[8], double (&rz)[8])
 {
+    // row0 = first bead of this lane's rows (row rb is row0 + 32 rb); coarse = (2 r_max)^2
     const double alpha = dm.alpha;
+    unsigned hits = 0u;                       // bit (qq * 4 + rb): pair within the coarse contact range
 #pragma unroll
     for (int qq = 0; qq < 8; qq++) {
         const int q = qg * 8 + qq;
         const double ox = __shfl_sync(0xffffffffu, cx, q), oy = __shfl_sync(0xffffffffu, cy, q),
                      oz = __shfl_sync(0xffffffffu, cz, q);
         double fx = 0.0, fy = 0.0, fz = 0.0;
-        unsigned hits = 0u;
 #pragma unroll
         for (int rb = 0; rb < 4; rb++) {
             const double dc = sd[(qq * 4 + rb) * 32], w = sd[1024 + (qq * 4 + rb) * 32];
@@ -787,30 +788,40 @@ __device__ __forceinline__ void backward_chunk(const DevModel &dm, const double 
             acc[rb][0] = fma(f, dx, acc[rb][0]); acc[rb][1] = fma(f, dy, acc[rb][1]); acc[rb][2] = fma(f, dz, acc[rb][2]);
             fx = fma(-f, dx, fx); fy = fma(-f, dy, fy); fz = fma(-f, dz, fz);
             if (NB) {
-                bool h = s2 < coarse[rb];
-                if (MASKED) h = h && (col0 + q > brow[rb]) && (col0 + q < dm.N) && (brow[rb] >= 0);
-                hits |= h ? (1u << rb) : 0u;
-            }
-        }
-        if (NB && __any_sync(0xffffffffu, hits != 0u)) {
-            // rare: some pair of this column is within the coarse contact range; redo those rows
-            const double ro = __shfl_sync(0xffffffffu, cr, q);
-#pragma unroll
-            for (int rb = 0; rb < 4; rb++) {
-                if (!__any_sync(0xffffffffu, (hits >> rb) & 1u)) continue;
-                double dx = ox - xb[rb][0], dy = oy - xb[rb][1], dz = oz - xb[rb][2];
-                double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                const double d0 = rr[rb] + ro;
-                if (((hits >> rb) & 1u) && s2 < d0 * d0) {
-                    const double rd = rsqrt_nr(s2);
-                    const double a = d0 - s2 * rd;
-                    const double g = nbs * ((a * a) * (a * rd));
-                    acc[rb][0] = fma(g, dx, acc[rb][0]); acc[rb][1] = fma(g, dy, acc[rb][1]); acc[rb][2] = fma(g, dz, acc[rb][2]);
-                    fx = fma(-g, dx, fx); fy = fma(-g, dy, fy); fz = fma(-g, dz, fz);
-                }
+                bool h = s2 < coarse;
+                if (MASKED) h = h && (col0 + q > row0 + 32 * rb) && (col0 + q < dm.N) && (row0 + 32 * rb < dm.N);
+                hits |= h ? (1u << (qq * 4 + rb)) : 0u;
             }
         }
         rx[qq] = fx; ry[qq] = fy; rz[qq] = fz;
+    }
+    if (NB) {
+        // rare: some pair of this chunk is within the coarse contact range.  One warp-wide OR
+        // decides; only the flagged (column, row) combinations are redone, in warp-uniform branches.
+        const unsigned any = __reduce_or_sync(0xffffffffu, hits);
+        if (any != 0u) {
+#pragma unroll
+            for (int qq = 0; qq < 8; qq++) {
+                if (((any >> (qq * 4)) & 15u) == 0u) continue;
+                const int q = qg * 8 + qq;
+                const double ox = __shfl_sync(0xffffffffu, cx, q), oy = __shfl_sync(0xffffffffu, cy, q),
+                             oz = __shfl_sync(0xffffffffu, cz, q), ro = __shfl_sync(0xffffffffu, cr, q);
+#pragma unroll
+                for (int rb = 0; rb < 4; rb++) {
+                    if (((any >> (qq * 4 + rb)) & 1u) == 0u) continue;
+                    double dx = ox - xb[rb][0], dy = oy - xb[rb][1], dz = oz - xb[rb][2];
+                    double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    const double d0 = dm.radii[min(row0 + 32 * rb, dm.N - 1)] + ro;
+                    if (((hits >> (qq * 4 + rb)) & 1u) && s2 < d0 * d0) {
+                        const double rd = rsqrt_nr(s2);
+                        const double a = d0 - s2 * rd;
+                        const double g = nbs * ((a * a) * (a * rd));
+                        acc[rb][0] = fma(g, dx, acc[rb][0]); acc[rb][1] = fma(g, dy, acc[rb][1]); acc[rb][2] = fma(g, dz, acc[rb][2]);
+                        rx[qq] = fma(-g, dx, rx[qq]); ry[qq] = fma(-g, dy, ry[qq]); rz[qq] = fma(-g, dz, rz[qq]);
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -828,18 +839,16 @@ backward_tile_kernel(DevModel dm, TileDev td, BackwardTileArgs ba)
     const long long rk = (long long)r * dm.S + (k_ok ? k : dm.S - 1);
     const int Np = dm.Np;
     const double *xk = ba.xs + rk * 3LL * Np;
-    int brow[4];
-    double xb[4][3], acc[4][3], rr[4], coarse[4];
+    const int row0 = 128 * I + lane;
+    double xb[4][3], acc[4][3];
 #pragma unroll
     for (int rb = 0; rb < 4; rb++) {
-        const int b0 = (4 * I + rb) * 32 + lane;
-        brow[rb] = b0 < dm.N ? b0 : -1;                   // -1: no such bead (loads use bead 0)
-        const int b = b0 < dm.N ? b0 : 0;
+        const int b0 = row0 + 32 * rb;
+        const int b = b0 < dm.N ? b0 : 0;                // rows past the last bead compute on bead 0, masked out
         xb[rb][0] = xk[b]; xb[rb][1] = xk[Np + b]; xb[rb][2] = xk[2 * Np + b];
         acc[rb][0] = acc[rb][1] = acc[rb][2] = 0.0;
-        rr[rb] = dm.radii[b];
-        coarse[rb] = (rr[rb] + ba.r_max) * (rr[rb] + ba.r_max);
     }
+    const double coarse = 4.0 * ba.r_max * ba.r_max;
     const double nbs = NB ? (ba.beta ? ba.beta[r] : 1.0) * 2.0 * dm.k_nb : 0.0;
     const double *twr = ba.tw + (long long)r * td.slots;
     double *Pk = ba.P + (rk * td.n_rb + I) * (long long)dm.N * 3;
@@ -883,8 +892,8 @@ backward_tile_kernel(DevModel dm, TileDev td, BackwardTileArgs ba)
         }
         const double *sd = smem + (c % EHIC_BT_STAGES) * 2048 + lane;
         double rx[8], ry[8], rz[8];
-        if (clean) backward_chunk<false, NB>(dm, sd, qg, lane, cx, cy, cz, cr, m, brow, col0, xb, rr, coarse, nbs, acc, rx, ry, rz);
-        else backward_chunk<true, NB>(dm, sd, qg, lane, cx, cy, cz, cr, m, brow, col0, xb, rr, coarse, nbs, acc, rx, ry, rz);
+        if (clean) backward_chunk<false, NB>(dm, sd, qg, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
+        else backward_chunk<true, NB>(dm, sd, qg, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
         reduce8(rx, lane); reduce8(ry, lane); reduce8(rz, lane);
         if ((lane & 3) == 0 && k_ok) {
             const int col = col0 + qg * 8 + (((lane >> 2) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 4) & 1));
@@ -895,7 +904,8 @@ backward_tile_kernel(DevModel dm, TileDev td, BackwardTileArgs ba)
     if (k_ok) {
 #pragma unroll
         for (int rb = 0; rb < 4; rb++) {
-            if (brow[rb] >= 0) { double *o = ba.Grow + (rk * dm.N + brow[rb]) * 3; o[0] = acc[rb][0]; o[1] = acc[rb][1]; o[2] = acc[rb][2]; }
+            const int b = row0 + 32 * rb;
+            if (b < dm.N) { double *o = ba.Grow + (rk * dm.N + b) * 3; o[0] = acc[rb][0]; o[1] = acc[rb][1]; o[2] = acc[rb][2]; }
         }
     }
 }
