@@ -64,6 +64,7 @@ struct ehic_model {
     double *energies = nullptr, *kinetic = nullptr;
     int nA = 0;                     // forward blocks per replica
     int nPx = 0;                    // prior blocks per structure
+    int prior_threads = 256;
     int cur_xt = 0;                 // which xt buffer matches the xs buffer handed to launch_forward
     int kt = 1, nkt = 1, nktg = 1;  // structures per warp, tiles per replica, tile groups (gw warps) per slice
     int gw = 4;                     // warps per gather CTA
@@ -243,7 +244,7 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     do { rc = upload(m, vec, &dm.field); if (rc) { ehic_model_destroy(m); return rc; } } while (0)
     UP(L.pi, pi); UP(L.pj, pj); UP(L.slot_a, slot_a); UP(L.slot_b, slot_b);
     UP(L.pdc, pdc); UP(L.pcnt, pcnt); UP(perm, perm);
-    UP(soff, slice_off); UP(L.slice_w, slice_w); UP(L.ent_j, ent_j); UP(L.ent_dc, ent_dc);
+    UP(soff, slice_off); UP(L.slice_w, slice_w); UP(L.ent_j, ent_j); UP(L.ent_dc, ent_dc); UP(L.row_bead, row_bead);
     UP(radii, radii); UP(ul, bb_ul); UP(ll, bb_ll);
 #undef UP
     if (m->use_tiles) {
@@ -270,7 +271,15 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     m->gw = pick_gw(m->nkt);
     m->nktg = (m->nkt + m->gw - 1) / m->gw;
     m->nA = (int)((L.M + 255) / 256);
-    m->nPx = (N + EHIC_PRIOR_THREADS - 1) / EHIC_PRIOR_THREADS;
+    {   // prior CTA size: the one that wastes the fewest thread slots on the last block of a structure
+        int best = 256; long long best_slots = 1LL << 60;
+        for (int t : {256, 128, 64}) {
+            long long slots = (long long)((N + t - 1) / t) * t;
+            if (slots < best_slots) { best_slots = slots; best = t; }
+        }
+        m->prior_threads = best;
+        m->nPx = (N + best - 1) / best;
+    }
     const size_t Rm = (size_t)desc->max_replicas;
     const size_t xs_n = Rm * S * 3 * (size_t)dm.Np;
 #define DA(ptr, n)                                                   \
@@ -437,10 +446,18 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
     dim3 grid((unsigned)m->nPx, (unsigned)m->dm.S, (unsigned)R);
     double *gp = want_grad ? m->gprior : nullptr, *pp = want_energy ? m->partP : nullptr;
     KernelTimer kt_(m, KC_PRIOR, st);
-    if (m->flags & EHIC_FLAG_EXACT)
-        prior_kernel<true><<<grid, EHIC_PRIOR_THREADS, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max);
-    else
-        prior_kernel<false><<<grid, EHIC_PRIOR_THREADS, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max);
+    const bool ex = (m->flags & EHIC_FLAG_EXACT) != 0;
+#define PK(T)                                                                                         \
+    do {                                                                                              \
+        if (ex) prior_kernel<true, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max);   \
+        else prior_kernel<false, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max);     \
+    } while (0)
+    switch (m->prior_threads) {
+    case 64: PK(64); break;
+    case 128: PK(128); break;
+    default: PK(256); break;
+    }
+#undef PK
     LAUNCHED();
     CU(cudaGetLastError());
     return EHIC_OK;

@@ -28,6 +28,7 @@ struct DevModel {
     const int *slice_w;
     const int *ent_j;
     const double *ent_dc;
+    const int *row_bead;    // [n_slices*32] lane slot -> bead (-1 = none)
     // per bead
     const double *radii;    // [N]
     const double *bb_ul;    // [N] upper limit of bond (b, b+1); +inf where there is no bond
@@ -221,9 +222,9 @@ __device__ __forceinline__ void load_record(const double *__restrict__ p, double
 // forcefield_c.pyx:47-57 accumulates into res[b].
 // Output: gprior[R][S][N][3] = beta * dE_nb/dx + d(-log p_bb)/dx + d(-log p_sphere)/dx and
 // per-CTA energy partials partP[(r*S+k)*gridDim.x + blockIdx.x][3] = (sum a^4, sum bb, sum sph).
-#define EHIC_PRIOR_THREADS 256
+#define EHIC_PRIOR_MAX_THREADS 256
 
-template <bool EXACT>
+template <bool EXACT, int EHIC_PRIOR_THREADS>
 __global__ void __launch_bounds__(EHIC_PRIOR_THREADS)
 prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restrict__ beta,
              double *__restrict__ gprior, double *__restrict__ partP, int terms, double r_max)
@@ -435,8 +436,8 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
     const int n_warps = blockDim.x >> 5;
     const int kt = ktg * n_warps + warp;
     const bool kt_ok = kt < nkt;
-    const int b = sl * 32 + lane;
-    const bool bead_ok = b < dm.N;
+    const int b = dm.row_bead[sl * 32 + lane];
+    const bool bead_ok = b >= 0;
     const int bb = bead_ok ? b : dm.N - 1;
     const int Np = dm.Np;
     const long long plane = 3LL * Np;

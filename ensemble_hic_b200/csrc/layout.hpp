@@ -39,6 +39,8 @@ struct ContactLayout {
     std::vector<int64_t> slice_off;   // n_slices + 1, in entries
     std::vector<int32_t> slice_w;     // n_slices
     std::vector<int32_t> row_len;     // N
+    std::vector<int32_t> row_bead;    // n_slices * 32: bead handled by each lane slot (-1 = none).  Identity
+                                      // for near-uniform rows; sorted by row length when that saves padding.
     std::vector<int32_t> ent_j;       // tot + kTailPad; padding slots hold a harmless partner (weight 0)
     std::vector<double> ent_dc;       // tot + kTailPad
     int64_t tot = 0;                  // slots that belong to slices (multiple of 32)
@@ -163,11 +165,31 @@ inline std::string build_layout(int32_t N, int64_t M, const int64_t *data, const
     L.row_len.assign(N, 0);
     for (int64_t s = 0; s < M; s++) { L.row_len[L.pi[s]]++; L.row_len[L.pj[s]]++; }
     L.n_slices = (N + 31) / 32;
+    // lane slot -> bead: identity, unless sorting the beads by row length (SELL-C-sigma with
+    // sigma = N) saves more than 10 % of the padded slots (ragged lists such as nora2012)
+    L.row_bead.assign((size_t)L.n_slices * 32, -1);
+    for (int32_t b = 0; b < N; b++) L.row_bead[b] = b;
+    auto padded = [&](const std::vector<int32_t> &rb) {
+        int64_t tot = 0;
+        for (int32_t sl = 0; sl < L.n_slices; sl++) {
+            int32_t w = 0;
+            for (int32_t l = 0; l < 32; l++) { int32_t b = rb[(size_t)sl * 32 + l]; if (b >= 0) w = std::max(w, L.row_len[b]); }
+            tot += (int64_t)32 * w;
+        }
+        return tot;
+    };
+    {
+        std::vector<int32_t> sorted(L.row_bead);
+        std::stable_sort(sorted.begin(), sorted.begin() + N, [&](int32_t a, int32_t b) { return L.row_len[a] > L.row_len[b]; });
+        if ((double)padded(sorted) < 0.9 * (double)padded(L.row_bead)) L.row_bead.swap(sorted);
+    }
+    std::vector<int32_t> slot_of_bead(N);
+    for (size_t q = 0; q < L.row_bead.size(); q++) if (L.row_bead[q] >= 0) slot_of_bead[L.row_bead[q]] = (int32_t)q;
     L.slice_off.assign(L.n_slices + 1, 0);
     L.slice_w.assign(L.n_slices, 0);
     for (int32_t sl = 0; sl < L.n_slices; sl++) {
         int32_t w = 0;
-        for (int32_t b = sl * 32; b < std::min(N, sl * 32 + 32); b++) w = std::max(w, L.row_len[b]);
+        for (int32_t l = 0; l < 32; l++) { int32_t b = L.row_bead[(size_t)sl * 32 + l]; if (b >= 0) w = std::max(w, L.row_len[b]); }
         L.slice_w[sl] = w;
         L.slice_off[sl + 1] = L.slice_off[sl] + (int64_t)32 * w;
     }
@@ -180,15 +202,16 @@ inline std::string build_layout(int32_t N, int64_t M, const int64_t *data, const
     for (int32_t sl = 0; sl < L.n_slices; sl++)
         for (int32_t e = 0; e < L.slice_w[sl]; e++)
             for (int32_t lane = 0; lane < 32; lane++) {
-                int32_t b = sl * 32 + lane;
-                int32_t pad = (b >= N) ? 0 : (b + 1 < N ? b + 1 : (b > 0 ? b - 1 : 0));
+                int32_t b = L.row_bead[(size_t)sl * 32 + lane];
+                int32_t pad = (b < 0) ? 0 : (b + 1 < N ? b + 1 : (b > 0 ? b - 1 : 0));
                 L.ent_j[L.slice_off[sl] + (int64_t)32 * e + lane] = pad;
             }
     if (want_values) L.ent_dc.assign(L.tot + ContactLayout::kTailPad, 0.0);
     L.slot_a.resize(M); L.slot_b.resize(M);
     std::vector<int32_t> fill(N, 0);
     auto place = [&](int32_t b, int32_t o, int64_t s, bool first) {
-        int64_t pos = L.slice_off[b / 32] + (int64_t)32 * fill[b] + (b % 32);
+        const int32_t sb = slot_of_bead[b];
+        int64_t pos = L.slice_off[sb / 32] + (int64_t)32 * fill[b] + (sb % 32);
         fill[b]++;
         L.ent_j[pos] = o;
         if (want_values) L.ent_dc[pos] = L.pdc[s];

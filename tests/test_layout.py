@@ -29,9 +29,12 @@ def test_sorted_contact_list_is_bitexact(seed, N, density, exact):
     assert np.array_equal(srt, expect)
     deg = np.bincount(data[:, 0], minlength=N) + np.bincount(data[:, 1], minlength=N)
     assert np.array_equal(rl, deg)
-    # sliced-ELL slots: 32 lanes x max row length per slice of 32 beads
-    exp_slots = sum(32 * int(deg[s:s + 32].max()) for s in range(0, N, 32))
-    assert slots == exp_slots
+    # sliced-ELL slots: 32 lanes x max row length per slice of 32 lane slots; beads keep their index
+    # order unless sorting them by row length saves more than 10 % of the padded slots
+    ident = sum(32 * int(deg[s:s + 32].max()) for s in range(0, N, 32))
+    srt_deg = np.sort(deg, kind="stable")[::-1]
+    by_len = sum(32 * int(srt_deg[s:s + 32].max()) for s in range(0, N, 32))
+    assert slots == (by_len if by_len < 0.9 * ident else ident)
 
 
 def test_empty_and_tiny_lists():
