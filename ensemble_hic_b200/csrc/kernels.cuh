@@ -223,6 +223,7 @@ __device__ __forceinline__ void load_record(const double *__restrict__ p, double
 // Output: gprior[R][S][N][3] = beta * dE_nb/dx + d(-log p_bb)/dx + d(-log p_sphere)/dx and
 // per-CTA energy partials partP[(r*S+k)*gridDim.x + blockIdx.x][3] = (sum a^4, sum bb, sum sph).
 #define EHIC_PRIOR_MAX_THREADS 256
+#define EHIC_PRIOR_TILE 512
 
 template <bool EXACT, int EHIC_PRIOR_THREADS>
 __global__ void __launch_bounds__(EHIC_PRIOR_THREADS)
@@ -241,23 +242,59 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
     double e_nb = 0.0, e_bb = 0.0, e_sp = 0.0;
 
     if (terms & 2) {
-        __shared__ double2 sxy[EHIC_PRIOR_THREADS];
-        __shared__ double2 szr[EHIC_PRIOR_THREADS];
+        // partner tile: EHIC_PRIOR_TILE beads as (x, y), (z, radius), independent of the CTA size so
+        // that small systems need one or two barriers per structure
+        __shared__ double2 sxy[EHIC_PRIOR_TILE];
+        __shared__ double2 szr[EHIC_PRIOR_TILE];
         const double rb2 = __dmul_rn(rb, rb);
         const double coarse = (rb + r_max) * (rb + r_max);
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int t0 = 0; t0 < dm.N; t0 += EHIC_PRIOR_THREADS) {
+        for (int t0 = 0; t0 < dm.N; t0 += EHIC_PRIOR_TILE) {
             __syncthreads();
-            {
-                int o = t0 + threadIdx.x;
+            for (int q = threadIdx.x; q < EHIC_PRIOR_TILE; q += EHIC_PRIOR_THREADS) {
+                int o = t0 + q;
                 int oo = o < dm.N ? o : dm.N - 1;
-                sxy[threadIdx.x] = make_double2(xk[oo], xk[Np + oo]);
-                szr[threadIdx.x] = make_double2(xk[2 * Np + oo], dm.radii[oo]);
+                sxy[q] = make_double2(xk[oo], xk[Np + oo]);
+                szr[q] = make_double2(xk[2 * Np + oo], dm.radii[oo]);
             }
             __syncthreads();
-            const int cnt = min(EHIC_PRIOR_THREADS, dm.N - t0);
+            const int cnt = min(EHIC_PRIOR_TILE, dm.N - t0);
+            if (!EXACT) {
+                // fast mode: the all-pairs sweep only TESTS (6 FP64 + compare per pair, branch-free,
+                // 32 partners per bit mask); the few partners within the coarse contact range are
+                // then evaluated from the mask, in ascending order
+                for (int q0 = 0; q0 < cnt; q0 += 32) {
+                    unsigned hits = 0u;
+#pragma unroll
+                    for (int qq = 0; qq < 32; qq++) {
+                        const double2 pxy = sxy[q0 + qq], pzr = szr[q0 + qq];     // tile is padded: always readable
+                        double dx = pxy.x - xb0, dy = pxy.y - xb1, dz = pzr.x - xb2;
+                        double s = fma(dz, dz, fma(dy, dy, dx * dx));
+                        hits |= (s < coarse) ? (1u << qq) : 0u;
+                    }
+                    const int self = b - (t0 + q0);
+                    if (self >= 0 && self < 32) hits &= ~(1u << self);
+                    if (q0 + 32 > cnt) hits &= (cnt - q0 >= 32) ? 0xffffffffu : ((1u << (cnt - q0)) - 1u);
+                    while (hits) {
+                        const int qq = __ffs(hits) - 1;
+                        hits &= hits - 1u;
+                        const double2 pxy = sxy[q0 + qq], pzr = szr[q0 + qq];
+                        double dx = pxy.x - xb0, dy = pxy.y - xb1, dz = pzr.x - xb2;
+                        double s = fma(dz, dz, fma(dy, dy, dx * dx));
+                        double d0s = rb + pzr.y;
+                        if (s < d0s * d0s) {
+                            double rd = rsqrt_nr(s);
+                            double a = d0s - s * rd;
+                            double aa = a * a;
+                            double g = aa * a * rd;
+                            a0 = fma(g, dx, a0); a1 = fma(g, dy, a1); a2 = fma(g, dz, a2);
+                            e_nb += aa * aa;
+                        }
+                    }
+                }
+            }
 #pragma unroll 4
-            for (int q = 0; q < cnt; q++) {
+            for (int q = 0; EXACT && q < cnt; q++) {
                 const double2 pxy = sxy[q], pzr = szr[q];
                 const int o = t0 + q;
                 if (EXACT) {
@@ -275,20 +312,6 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
                         a2 = __dadd_rn(a2, __dmul_rn(__dsub_rn(pzr.x, xb2), g));
                         double aa = a * a;
                         e_nb += aa * aa;
-                    }
-                } else {
-                    double dx = pxy.x - xb0, dy = pxy.y - xb1, dz = pzr.x - xb2;
-                    double s = fma(dz, dz, fma(dy, dy, dx * dx));
-                    if (s < coarse && o != b) {
-                        double d0s = rb + pzr.y;
-                        if (s < d0s * d0s) {
-                            double rd = rsqrt_nr(s);
-                            double a = d0s - s * rd;
-                            double aa = a * a;
-                            double g = aa * a * rd;
-                            a0 = fma(g, dx, a0); a1 = fma(g, dy, a1); a2 = fma(g, dz, a2);
-                            e_nb += aa * aa;
-                        }
                     }
                 }
             }
