@@ -69,6 +69,9 @@ struct ehic_model {
     int kt = 1, nkt = 1, nktg = 1;  // structures per warp, tiles per replica, tile groups (gw warps) per slice
     int gw = 4;                     // warps per gather CTA
     double r_max = 0.0;
+    // CUDA graphs of whole HMC trajectories, keyed by the call signature; dropped when a parameter changes
+    struct TrajGraph { std::vector<const void *> key; cudaGraphExec_t exec; long long n_kernels; };
+    std::vector<TrajGraph> graphs;
     // optional per-kernel timing (ehic_profile): events bracket every launch on its stream
     bool profiling = false;
     struct Timed { int cls; cudaEvent_t a, b; };
@@ -77,6 +80,12 @@ struct ehic_model {
     double *st_x = nullptr, *st_g = nullptr, *st_md = nullptr, *st_small = nullptr;
     cudaStream_t st_stream = nullptr;
 };
+
+static void drop_graphs(ehic_model *m)
+{
+    for (auto &g : m->graphs) cudaGraphExecDestroy(g.exec);
+    m->graphs.clear();
+}
 
 KernelTimer::KernelTimer(ehic_model *m_, int cls, cudaStream_t st_) : m(m_), st(st_), idx(-1)
 {
@@ -338,6 +347,7 @@ int ehic_model_destroy(ehic_model_t *m)
 {
     if (!m) return EHIC_OK;
     cudaSetDevice(m->device);
+    drop_graphs(m);
     for (void *p : m->owned) cudaFree(p);
     cudaFree(m->st_x); cudaFree(m->st_g); cudaFree(m->st_md); cudaFree(m->st_small);
     if (m->st_stream) cudaStreamDestroy(m->st_stream);
@@ -348,6 +358,9 @@ int ehic_model_destroy(ehic_model_t *m)
 int ehic_model_set_param(ehic_model_t *m, int which, double v)
 {
     if (!m) return fail(EHIC_ERR_INVALID, "null model");
+    double cur = 0.0;
+    if (ehic_model_get_param(m, which, &cur) == EHIC_OK && cur == v) return EHIC_OK;
+    drop_graphs(m);       // kernel arguments are baked into captured graphs
     switch (which) {
     case EHIC_PARAM_ALPHA: m->dm.alpha = v; break;
     case EHIC_PARAM_NONBONDED_K: m->dm.k_nb = v; break;
@@ -580,6 +593,10 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     return EHIC_OK;
 }
 
+static int enqueue_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double *d_p,
+                              const double *d_norm, const double *d_lammda, const double *d_beta,
+                              const double *d_eps, double *d_H, cudaStream_t st);
+
 int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double *d_p,
                         const double *d_norm, const double *d_lammda, const double *d_beta,
                         const double *d_eps, double *d_H, void *stream)
@@ -589,6 +606,59 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
     if (!d_x || !d_p || !d_norm || !d_eps || !d_H) return fail(EHIC_ERR_INVALID, "null buffer");
     if (n_steps < 1) return fail(EHIC_ERR_INVALID, "n_steps must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool use_graphs = []() { const char *e = getenv("EHIC_GRAPH"); return !(e && !strcmp(e, "0")); }();
+    if (!use_graphs || m->profiling)
+        return enqueue_trajectory(m, R, n_steps, d_x, d_p, d_norm, d_lammda, d_beta, d_eps, d_H, st);
+    // One graph launch per proposal: the 3 (L+1) + few kernels of a trajectory are captured once per
+    // call signature and replayed, which removes the per-kernel launch latency that dominates the
+    // small configurations (hairpin_s, proteins).
+    std::vector<const void *> key = {(const void *)(intptr_t)R, (const void *)(intptr_t)n_steps, d_x, d_p, d_norm,
+                                     d_lammda, d_beta, d_eps, d_H};
+    for (auto &g : m->graphs)
+        if (g.key == key) {
+            CU(cudaGraphLaunch(g.exec, st));
+            g_launches.fetch_add(g.n_kernels, std::memory_order_relaxed);
+            return EHIC_OK;
+        }
+    // capture on the model's own stream (the legacy default stream cannot be captured)
+    cudaStream_t cs = m->st_stream;
+    const long long before = g_launches.load();
+    if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return enqueue_trajectory(m, R, n_steps, d_x, d_p, d_norm, d_lammda, d_beta, d_eps, d_H, st);
+    }
+    rc = enqueue_trajectory(m, R, n_steps, d_x, d_p, d_norm, d_lammda, d_beta, d_eps, d_H, cs);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    const long long n_kernels = g_launches.load() - before;
+    g_launches.store(before);
+    if (rc != EHIC_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc != EHIC_OK) return rc;
+        return enqueue_trajectory(m, R, n_steps, d_x, d_p, d_norm, d_lammda, d_beta, d_eps, d_H, st);
+    }
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        return enqueue_trajectory(m, R, n_steps, d_x, d_p, d_norm, d_lammda, d_beta, d_eps, d_H, st);
+    }
+    if (m->graphs.size() >= 8) { cudaGraphExecDestroy(m->graphs.front().exec); m->graphs.erase(m->graphs.begin()); }
+    m->graphs.push_back({key, exec, n_kernels});
+    CU(cudaGraphLaunch(exec, st));
+    g_launches.fetch_add(n_kernels, std::memory_order_relaxed);
+    return EHIC_OK;
+}
+
+}  // extern "C"
+
+static int enqueue_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double *d_p,
+                              const double *d_norm, const double *d_lammda, const double *d_beta,
+                              const double *d_eps, double *d_H, cudaStream_t st)
+{
+    int rc = EHIC_OK;
     int prior_terms = EHIC_TERM_ALL & ~EHIC_TERM_LIKELIHOOD;
     if (!m->dm.sphere_active) prior_terms &= ~EHIC_TERM_SPHERE;
     rc = launch_pack(m, R, d_x, m->xs[0], m->xt[0], st);
@@ -631,6 +701,8 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
     CU(cudaGetLastError());
     return EHIC_OK;
 }
+
+extern "C" {
 
 int ehic_select(int R, int64_t n, const int32_t *d_mask, const double *d_src, double *d_dst, void *stream)
 {
