@@ -48,6 +48,7 @@ struct ehic_model {
     int max_replicas = 0;
     DevModel dm{};
     ContactLayout layout;           // host copy (sizes, perm)
+    bool traj_small_ready = false;
     bool use_tiles = false;         // dense list + fast mode: symmetric tile path
     bool nb_fused = false;          // tiles cover all bead pairs: nonbonded force rides in the backward tile kernel
     const unsigned char *tile_clean = nullptr;
@@ -606,6 +607,27 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
     if (!d_x || !d_p || !d_norm || !d_eps || !d_H) return fail(EHIC_ERR_INVALID, "null buffer");
     if (n_steps < 1) return fail(EHIC_ERR_INVALID, "n_steps must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
+    // small systems: the whole trajectory in ONE kernel launch, state resident in shared memory
+    {
+        const char *tj = getenv("EHIC_TRAJ");
+        const size_t sm = sizeof(double) * ((size_t)m->dm.S * m->dm.N * 3 + (size_t)m->dm.tot + 32);
+        const bool fits = sm <= 200 * 1024 && !(m->flags & EHIC_FLAG_EXACT);
+        if (fits && !(tj && !strcmp(tj, "multi")) && !m->profiling) {
+            if (!m->traj_small_ready) {
+                CU(cudaFuncSetAttribute(trajectory_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                m->traj_small_ready = true;
+            }
+            TrajSmallArgs ta{};
+            ta.x = d_x; ta.p = d_p; ta.norm = d_norm; ta.lammda = d_lammda; ta.beta = d_beta; ta.eps = d_eps;
+            ta.H = d_H; ta.n_steps = n_steps; ta.r_max = m->r_max;
+            const int items = m->dm.S * m->dm.n_slices * 32;
+            const int threads = items >= 512 || m->dm.M >= 512 ? 512 : (items > 128 || m->dm.M > 128 ? 256 : 128);
+            trajectory_small_kernel<<<R, threads, sm, st>>>(m->dm, ta);
+            LAUNCHED();
+            CU(cudaGetLastError());
+            return EHIC_OK;
+        }
+    }
     static const bool use_graphs = []() { const char *e = getenv("EHIC_GRAPH"); return !(e && !strcmp(e, "0")); }();
     if (!use_graphs || m->profiling)
         return enqueue_trajectory(m, R, n_steps, d_x, d_p, d_norm, d_lammda, d_beta, d_eps, d_H, st);

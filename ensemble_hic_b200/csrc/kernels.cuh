@@ -1058,6 +1058,179 @@ __global__ void select_kernel(int R, long long n, const int *__restrict__ mask,
 }
 
 // ---------------------------------------------------------------------------------------
+// Whole-trajectory kernel for SMALL systems (north-star kernel 3): ONE launch = one HMC proposal.
+// CTA <-> replica.  The replica's coordinates (all S structures) and the per-slot Poisson weights
+// live in shared memory for the whole trajectory, momenta in global memory (each element has one
+// owner thread).  Per leapfrog step: forward (thread <-> data point, serial over the ensemble),
+// barrier, gradient (thread <-> (structure, bead): contact row + all-pairs nonbonded + backbone +
+// sphere, same arithmetic as gather_kernel / prior_kernel in fast mode) fused with the kick,
+// barrier, drift, barrier.  Used when S*N*24 B + slots*8 B fits the 227 KB of one SM: hairpin_s,
+// proteins, nora2012 15 kb; larger systems take the multi-kernel path (captured in a CUDA graph).
+struct TrajSmallArgs {
+    double *x, *p;                 // [R][S][N][3] in/out
+    const double *norm, *lammda, *beta, *eps;
+    double *H;                     // [R][4]
+    int n_steps;
+    double r_max;
+};
+
+__device__ __forceinline__ double block_sum(double v, double *sh /* [32] */)
+{
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); q++) t += sh[q];
+    return t;
+}
+
+__global__ void __launch_bounds__(512)
+trajectory_small_kernel(DevModel dm, TrajSmallArgs ta)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int r = blockIdx.x;
+    const int N = dm.N, S = dm.S;
+    const int ndof = S * N * 3;
+    double *sx = smem;                         // [S][N][3]
+    double *sw = sx + ndof;                    // [tot] row-slot weights (lammda already applied)
+    double *red = sw + dm.tot;                 // [32]
+    double *gx = ta.x + (long long)r * ndof, *gp = ta.p + (long long)r * ndof;
+    const double nrm = ta.norm[r];
+    const double lam = ta.lammda ? ta.lammda[r] : 1.0, bet = ta.beta ? ta.beta[r] : 1.0;
+    const double eps = ta.eps[r];
+    const double alpha = dm.alpha;
+    const int n_slots = dm.n_slices * 32;
+
+    for (int q = threadIdx.x; q < ndof; q += blockDim.x) sx[q] = gx[q];
+    for (long long q = threadIdx.x; q < dm.tot; q += blockDim.x) sw[q] = 0.0;
+    __syncthreads();
+
+    for (int step = 0; step <= ta.n_steps; step++) {
+        const bool first = step == 0, last = step == ta.n_steps, ends = first || last;
+        // ---- forward: md, weights, log L ------------------------------------------------------
+        double logl = 0.0;
+        for (long long m = threadIdx.x; m < dm.M; m += blockDim.x) {
+            const int i = dm.pi[m], j = dm.pj[m];
+            const double dc = dm.pdc[m], c = dm.pcnt[m];
+            double acc = 0.0;
+            for (int k = 0; k < S; k++) {
+                const double *a = sx + (k * N + i) * 3, *b = sx + (k * N + j) * 3;
+                double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+                double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                double rd = rsqrt_nr(s2);
+                double tt = alpha * (dc - s2 * rd);
+                double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                acc += fma(tt, rq, 1.0);
+            }
+            const double md = acc * (0.5 * nrm);
+            const double em = 1.0 - c / md;
+            const double w = lam * (((0.5 * em) * nrm) * alpha);
+            sw[dm.slot_a[m]] = w; sw[dm.slot_b[m]] = w;
+            if (ends) logl += c * log(md) - md;
+        }
+        __syncthreads();
+        // ---- gradient of every (structure, bead) + kick ------------------------------------------
+        double e_nb = 0.0, e_bb = 0.0, e_sp = 0.0, kin = 0.0;
+        const double kick = (ends ? 0.5 : 1.0) * eps;
+        for (int item = threadIdx.x; item < S * n_slots; item += blockDim.x) {
+            const int k = item / n_slots, slot = item - k * n_slots;
+            const int b = dm.row_bead[slot];
+            if (b < 0) continue;
+            const double *xk = sx + k * N * 3;
+            const double xb0 = xk[3 * b], xb1 = xk[3 * b + 1], xb2 = xk[3 * b + 2];
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+            {   // contact row (weights carry lammda)
+                const int sl = slot >> 5, lane = slot & 31;
+                const long long off = dm.slice_off[sl] + lane;
+                const int width = dm.slice_w[sl];
+                for (int e = 0; e < width; e++) {
+                    const int o = dm.ent_j[off + 32 * e];
+                    const double dc = dm.ent_dc[off + 32 * e], w = sw[off + 32 * e];
+                    double dx = xk[3 * o] - xb0, dy = xk[3 * o + 1] - xb1, dz = xk[3 * o + 2] - xb2;
+                    double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    double rd = rsqrt_nr(s2);
+                    double tt = alpha * (dc - s2 * rd);
+                    double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                    double f = w * ((rq * rq) * (rq * rd));
+                    g0 = fma(f, dx, g0); g1 = fma(f, dy, g1); g2 = fma(f, dz, g2);
+                }
+            }
+            const double rb = dm.radii[b];
+            {   // nonbonded, all partners ascending
+                const double coarse = (rb + ta.r_max) * (rb + ta.r_max);
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+                for (int o = 0; o < N; o++) {
+                    double dx = xk[3 * o] - xb0, dy = xk[3 * o + 1] - xb1, dz = xk[3 * o + 2] - xb2;
+                    double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    if (s2 < coarse && o != b) {
+                        const double d0 = rb + dm.radii[o];
+                        if (s2 < d0 * d0) {
+                            double rd = rsqrt_nr(s2);
+                            double a = d0 - s2 * rd, aa = a * a;
+                            double g = aa * a * rd;
+                            a0 = fma(g, dx, a0); a1 = fma(g, dy, a1); a2 = fma(g, dz, a2);
+                            e_nb += aa * aa;
+                        }
+                    }
+                }
+                const double sc = bet * (dm.k_nb * 2.0);
+                g0 = fma(sc, a0, g0); g1 = fma(sc, a1, g1); g2 = fma(sc, a2, g2);
+            }
+            {   // backbone
+                double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+                if (b > 0 && !isinf(dm.bb_ul[b - 1])) {
+                    const double ul = dm.bb_ul[b - 1], ll = dm.bb_ll[b - 1];
+                    double d0 = xb0 - xk[3 * b - 3], d1 = xb1 - xk[3 * b - 2], d2 = xb2 - xk[3 * b - 1];
+                    double s2 = d0 * d0 + d1 * d1 + d2 * d2;
+                    if (s2 > ul * ul) { double d = sqrt(s2), a = d - ul; r0 = a * d0 / d; r1 = a * d1 / d; r2 = a * d2 / d; e_bb += a * a; }
+                    else if (s2 < ll * ll) { double d = sqrt(s2), a = ll - d; r0 = -(a * d0 / d); r1 = -(a * d1 / d); r2 = -(a * d2 / d); e_bb += a * a; }
+                }
+                if (!isinf(dm.bb_ul[b])) {
+                    const double ul = dm.bb_ul[b], ll = dm.bb_ll[b];
+                    double d0 = xk[3 * b + 3] - xb0, d1 = xk[3 * b + 4] - xb1, d2 = xk[3 * b + 5] - xb2;
+                    double s2 = d0 * d0 + d1 * d1 + d2 * d2;
+                    if (s2 > ul * ul) { double d = sqrt(s2), a = d - ul; r0 -= a * d0 / d; r1 -= a * d1 / d; r2 -= a * d2 / d; }
+                    else if (s2 < ll * ll) { double d = sqrt(s2), a = ll - d; r0 += a * d0 / d; r1 += a * d1 / d; r2 += a * d2 / d; }
+                }
+                g0 = fma(dm.k_bb, r0, g0); g1 = fma(dm.k_bb, r1, g1); g2 = fma(dm.k_bb, r2, g2);
+            }
+            if (dm.sphere_active) {
+                const double R0 = dm.sph_R;
+                double d0 = xb0 - dm.sph_cx, d1 = xb1 - dm.sph_cy, d2 = xb2 - dm.sph_cz;
+                double s2 = d0 * d0 + d1 * d1 + d2 * d2;
+                if (!(s2 < (R0 * R0 + rb * rb) - (2.0 * R0) * rb)) {
+                    double d = sqrt(s2), a = (d + rb) - R0, f = a / d;
+                    g0 = fma(dm.sph_k, d0 * f, g0); g1 = fma(dm.sph_k, d1 * f, g1); g2 = fma(dm.sph_k, d2 * f, g2);
+                    if (a > 0.0) e_sp += a * a;
+                }
+            }
+            const int at = (k * N + b) * 3;
+            double p0 = gp[at], p1 = gp[at + 1], p2 = gp[at + 2];
+            if (first) kin += p0 * p0 + p1 * p1 + p2 * p2;
+            p0 = fma(-kick, g0, p0); p1 = fma(-kick, g1, p1); p2 = fma(-kick, g2, p2);
+            gp[at] = p0; gp[at + 1] = p1; gp[at + 2] = p2;
+            if (last) kin += p0 * p0 + p1 * p1 + p2 * p2;
+        }
+        if (ends) {
+            const double tl = block_sum(logl, red), tn = block_sum(e_nb, red), tb = block_sum(e_bb, red),
+                         ts = block_sum(e_sp, red), tk = block_sum(kin, red);
+            if (threadIdx.x == 0) {
+                double *H = ta.H + (long long)r * 4 + (first ? 0 : 2);
+                H[0] = lam * (-tl) + bet * (0.25 * dm.k_nb * tn) + 0.5 * dm.k_bb * tb + 0.5 * dm.sph_k * ts;
+                H[1] = 0.5 * tk;
+            }
+        }
+        __syncthreads();                       // everybody is done reading sx
+        if (!last) {
+            for (int q = threadIdx.x; q < ndof; q += blockDim.x) sx[q] = fma(eps, gp[q], sx[q]);
+            __syncthreads();
+        }
+    }
+    for (int q = threadIdx.x; q < ndof; q += blockDim.x) gx[q] = sx[q];
+}
+
+// ---------------------------------------------------------------------------------------
 // Neighbour list of one structure (c/nblist.c:181-303): membership |dx|^2 <= cutoff^2 with
 // the dot product associated as mathutils.c:13-15 and no FMA contraction.
 __global__ void nblist_count_kernel(const double *__restrict__ x, int N, double cut2, int *__restrict__ counts)

@@ -252,6 +252,7 @@ def test_tile_path_trajectory(co, monkeypatch):
     import torch
     from oracle.oracle import OraclePosterior, leapfrog
     monkeypatch.setenv("EHIC_PATH", "tiles")
+    monkeypatch.setenv("EHIC_TRAJ", "multi")          # the multi-kernel (CUDA graph) trajectory, not the one-CTA kernel
     pb = make_problem(seed=77, S=3, N=140, step=0.8)
     N, S = pb["N"], pb["S"]
     ul = pb["radii"][:-1] + pb["radii"][1:]
@@ -276,3 +277,35 @@ def test_tile_path_trajectory(co, monkeypatch):
         E1 = -op.log_prob(x1, norm[r], lam[r], bet[r])
         assert abs(H[r, 2] - E1) <= 1e-10 * abs(E1)
         assert abs(H[r, 3] - 0.5 * np.sum(p1 ** 2)) <= 1e-9 * H[r, 3]
+
+
+@pytest.mark.parametrize("S,N,density,sphere", [(2, 23, 1.0, True), (2, 56, 1.0, True), (10, 62, 0.5, False), (1, 40, 0.3, False)])
+def test_one_launch_trajectory_equals_multi_kernel_trajectory(monkeypatch, S, N, density, sphere):
+    """small systems: whole trajectory in one kernel (state in shared memory) vs the kernel-per-phase path"""
+    import torch
+    pb = make_problem(seed=S + N, S=S, N=N, density=density, radius=1.0, cd_factor=2.0, min_sep=2, step=1.8)
+    R, L = 3, 25
+    rng = np.random.default_rng(4)
+    X = np.stack([pb["X"] + rng.normal(scale=0.05, size=pb["X"].shape) for _ in range(R)]).reshape(R, -1)
+    P = rng.normal(size=X.shape)
+    norm = np.array([2.5, 3.5, 1.5]); lam = np.array([0.3, 1.0, 0.0]); bet = np.array([0.5, 1.0, 0.01]); eps = np.array([1e-3, 2e-3, 5e-3])
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    res = {}
+    for mode in ("multi", "small"):
+        if mode == "multi":
+            monkeypatch.setenv("EHIC_TRAJ", "multi")
+        else:
+            monkeypatch.delenv("EHIC_TRAJ", raising=False)
+        m = _model(pb, False, k_nb=50.0, k_bb=1000.0, sphere=(10.0, 5.0, np.zeros(3)) if sphere else None, max_replicas=R)
+        x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
+        from ensemble_hic_b200.engine import launch_count
+        l0 = launch_count()
+        m.hmc_trajectory_device(R, L, x_t, p_t, t(norm), t(lam), t(bet), t(eps), H_t)
+        torch.cuda.synchronize()
+        res[mode] = (x_t.cpu().numpy(), p_t.cpu().numpy(), H_t.cpu().numpy(), launch_count() - l0)
+        m.close()
+    assert res["small"][3] == 1 and res["multi"][3] > 3 * L
+    assert relerr(res["small"][0], res["multi"][0]) < 1e-12
+    assert relerr(res["small"][1], res["multi"][1]) < 1e-10
+    np.testing.assert_allclose(res["small"][2], res["multi"][2], rtol=1e-11)
