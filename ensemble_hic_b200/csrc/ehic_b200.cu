@@ -622,6 +622,9 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
             ta.H = d_H; ta.n_steps = n_steps; ta.r_max = m->r_max;
             const int items = m->dm.S * m->dm.n_slices * 32;
             const int threads = items >= 512 || m->dm.M >= 512 ? 512 : (items > 128 || m->dm.M > 128 ? 256 : 128);
+            int split = 1;
+            while (split < 32 && items * split * 2 <= threads) split *= 2;
+            ta.split = split;
             trajectory_small_kernel<<<R, threads, sm, st>>>(m->dm, ta);
             LAUNCHED();
             CU(cudaGetLastError());

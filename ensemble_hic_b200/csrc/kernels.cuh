@@ -1072,6 +1072,7 @@ struct TrajSmallArgs {
     double *H;                     // [R][4]
     int n_steps;
     double r_max;
+    int split;                     // threads per (structure, bead) item: power of two <= 32
 };
 
 __device__ __forceinline__ double block_sum(double v, double *sh /* [32] */)
@@ -1133,18 +1134,25 @@ trajectory_small_kernel(DevModel dm, TrajSmallArgs ta)
         // ---- gradient of every (structure, bead) + kick ------------------------------------------
         double e_nb = 0.0, e_bb = 0.0, e_sp = 0.0, kin = 0.0;
         const double kick = (ends ? 0.5 : 1.0) * eps;
-        for (int item = threadIdx.x; item < S * n_slots; item += blockDim.x) {
-            const int k = item / n_slots, slot = item - k * n_slots;
-            const int b = dm.row_bead[slot];
-            if (b < 0) continue;
+        // each item (structure, bead) is shared by T = split adjacent lanes: lane `sub` takes every
+        // T-th row entry / partner; the partial forces are combined with xor shuffles (fixed order)
+        const int T = ta.split, sub = threadIdx.x & (T - 1);
+        const int groups = blockDim.x / T;
+        for (int base = 0; base < S * n_slots; base += groups) {
+            const int item = base + threadIdx.x / T;
+            const int k = item < S * n_slots ? item / n_slots : 0;
+            const int slot = item < S * n_slots ? item - k * n_slots : 0;
+            const int b_raw = item < S * n_slots ? dm.row_bead[slot] : -1;
+            const bool valid = b_raw >= 0;
+            const int b = valid ? b_raw : 0;
             const double *xk = sx + k * N * 3;
             const double xb0 = xk[3 * b], xb1 = xk[3 * b + 1], xb2 = xk[3 * b + 2];
             double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-            {   // contact row (weights carry lammda)
+            if (valid) {   // contact row (weights carry lammda)
                 const int sl = slot >> 5, lane = slot & 31;
                 const long long off = dm.slice_off[sl] + lane;
                 const int width = dm.slice_w[sl];
-                for (int e = 0; e < width; e++) {
+                for (int e = sub; e < width; e += T) {
                     const int o = dm.ent_j[off + 32 * e];
                     const double dc = dm.ent_dc[off + 32 * e], w = sw[off + 32 * e];
                     double dx = xk[3 * o] - xb0, dy = xk[3 * o + 1] - xb1, dz = xk[3 * o + 2] - xb2;
@@ -1157,10 +1165,10 @@ trajectory_small_kernel(DevModel dm, TrajSmallArgs ta)
                 }
             }
             const double rb = dm.radii[b];
-            {   // nonbonded, all partners ascending
+            if (valid) {   // nonbonded, partners sub, sub + T, ...
                 const double coarse = (rb + ta.r_max) * (rb + ta.r_max);
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-                for (int o = 0; o < N; o++) {
+                for (int o = sub; o < N; o += T) {
                     double dx = xk[3 * o] - xb0, dy = xk[3 * o + 1] - xb1, dz = xk[3 * o + 2] - xb2;
                     double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
                     if (s2 < coarse && o != b) {
@@ -1177,6 +1185,12 @@ trajectory_small_kernel(DevModel dm, TrajSmallArgs ta)
                 const double sc = bet * (dm.k_nb * 2.0);
                 g0 = fma(sc, a0, g0); g1 = fma(sc, a1, g1); g2 = fma(sc, a2, g2);
             }
+            for (int o = 1; o < T; o <<= 1) {      // all lanes of the warp take part: trip count is uniform
+                g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+                g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+                g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+            }
+            if (!valid || sub != 0) continue;     // lane 0 of the group finishes the bead
             {   // backbone
                 double r0 = 0.0, r1 = 0.0, r2 = 0.0;
                 if (b > 0 && !isinf(dm.bb_ul[b - 1])) {
