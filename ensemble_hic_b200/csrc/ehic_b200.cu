@@ -60,7 +60,7 @@ struct ehic_model {
     // workspace
     double *xs[2] = {nullptr, nullptr};   // SoA working copies (forward + prior kernels)
     double *xt[2] = {nullptr, nullptr};   // tile-AoS working copies (gather kernel)
-    double *wbuf = nullptr, *gprior = nullptr;
+    double *wbuf = nullptr, *gprior = nullptr, *bbox = nullptr;
     double *partA = nullptr, *partP = nullptr, *partK = nullptr;
     double *energies = nullptr, *kinetic = nullptr;
     int nA = 0;                     // forward blocks per replica
@@ -269,7 +269,9 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         UPT(TL.mask, mask); UPT(TL.dc, dc); UPT(TL.cnt, cnt); UPT(orig, orig);
 #undef UPT
         rc = upload(m, TL.clean, &m->tile_clean); if (rc) { ehic_model_destroy(m); return rc; }
-        { const char *nf = getenv("EHIC_NB_FUSED"); m->nb_fused = TL.covers_all_pairs && !(nf && !strcmp(nf, "0")); }
+        // fusing the nonbonded force into the backward tile kernel is off by default: with slice bounding-box
+        // pruning the separate prior kernel is cheaper than the extra registers the fused variant needs
+        { const char *nf = getenv("EHIC_NB_FUSED"); m->nb_fused = TL.covers_all_pairs && nf && !strcmp(nf, "1"); }
     }
     // free the big host vectors we no longer need
     std::vector<int32_t>().swap(L.ent_j); std::vector<double>().swap(L.ent_dc);
@@ -301,6 +303,7 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         if (cudaMemset(m->xt[q], 0, xt_n * sizeof(double)) != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed"); }
     DA(m->wbuf, Rm * (size_t)dm.wstride);
     DA(m->gprior, Rm * S * (size_t)N * 3);
+    DA(m->bbox, Rm * S * (size_t)L.n_slices * 6);
     DA(m->partA, Rm * (size_t)std::max(m->nA, 1));
     DA(m->partP, Rm * (size_t)S * m->nPx * 3);
     DA(m->partK, Rm * (size_t)L.n_slices * m->nktg * m->gw);
@@ -461,10 +464,15 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
     double *gp = want_grad ? m->gprior : nullptr, *pp = want_energy ? m->partP : nullptr;
     KernelTimer kt_(m, KC_PRIOR, st);
     const bool ex = (m->flags & EHIC_FLAG_EXACT) != 0;
+    if (terms & EHIC_TERM_NONBONDED) {
+        dim3 gb((unsigned)m->dm.n_slices, (unsigned)((long long)R * m->dm.S));
+        bbox_kernel<<<gb, 32, 0, st>>>(xs, m->bbox, m->dm.N, m->dm.Np, m->dm.n_slices);
+        LAUNCHED();
+    }
 #define PK(T)                                                                                         \
     do {                                                                                              \
-        if (ex) prior_kernel<true, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max);   \
-        else prior_kernel<false, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max);     \
+        if (ex) prior_kernel<true, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max, m->bbox);   \
+        else prior_kernel<false, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max, m->bbox);     \
     } while (0)
     switch (m->prior_threads) {
     case 64: PK(64); break;
@@ -498,6 +506,12 @@ static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_
             BackwardTileArgs ba{};
             ba.xs = ga.xs_cur; ba.tw = m->tw; ba.beta = ga.beta; ba.Grow = m->Grow; ba.P = m->Pbuf;
             ba.tile_clean = m->tile_clean; ba.n_kg = (m->dm.S + 3) / 4; ba.nb = ga.nb_fused; ba.r_max = m->r_max;
+            ba.bbox = m->bbox;
+            if (ga.nb_fused) {
+                dim3 gb((unsigned)m->dm.n_slices, (unsigned)((long long)R * m->dm.S));
+                bbox_kernel<<<gb, 32, 0, st>>>(ga.xs_cur, m->bbox, m->dm.N, m->dm.Np, m->dm.n_slices);
+                LAUNCHED();
+            }
             const unsigned blocks = (unsigned)((long long)R * m->td.n_rb * ba.n_kg);
             const size_t sm = EHIC_BT_STAGES * 2048 * sizeof(double);
             if (ga.nb_fused) backward_tile_kernel<true><<<blocks, 128, sm, st>>>(m->dm, m->td, ba);

@@ -212,6 +212,37 @@ __device__ __forceinline__ void load_record(const double *__restrict__ p, double
 }
 
 // ---------------------------------------------------------------------------------------
+// Bounding boxes of the 32-bead slices of every structure: bbox[R*S][n_slices][6] = (lo, hi).
+// Consecutive beads of a chain are neighbours in space, so the all-pairs sweep of the prior kernel
+// can discard whole 32 x 32 slice pairs whose boxes are farther apart than the largest contact
+// range (a warp-uniform test) -- the same pruning a cell grid gives the reference (c/nblist.c),
+// without sorting and without changing which pairs contribute or in which order.
+__global__ void __launch_bounds__(32)
+bbox_kernel(const double *__restrict__ xs, double *__restrict__ bbox, int N, int Np, int n_slices)
+{
+    const long long rk = blockIdx.y;
+    const int sl = blockIdx.x, lane = threadIdx.x;
+    const int b = min(sl * 32 + lane, N - 1);
+    const double *xk = xs + rk * 3LL * Np;
+    double lo[3], hi[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        double v = xk[c * Np + b];
+        double mn = v, mx = v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        lo[c] = mn; hi[c] = mx;
+    }
+    if (lane == 0) {
+        double *o = bbox + (rk * n_slices + sl) * 6;
+        o[0] = lo[0]; o[1] = lo[1]; o[2] = lo[2]; o[3] = hi[0]; o[4] = hi[1]; o[5] = hi[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Prior kernel (north-star kernel 2): repulsive nonbonded term as a tiled all-pairs gather,
 // with the backbone and sphere terms fused into the same pass.
 //
@@ -228,7 +259,8 @@ __device__ __forceinline__ void load_record(const double *__restrict__ p, double
 template <bool EXACT, int EHIC_PRIOR_THREADS>
 __global__ void __launch_bounds__(EHIC_PRIOR_THREADS)
 prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restrict__ beta,
-             double *__restrict__ gprior, double *__restrict__ partP, int terms, double r_max)
+             double *__restrict__ gprior, double *__restrict__ partP, int terms, double r_max,
+             const double *__restrict__ bbox)
 {
     const int k = blockIdx.y, r = blockIdx.z;
     const int b = blockIdx.x * EHIC_PRIOR_THREADS + threadIdx.x;
@@ -246,8 +278,15 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
         // that small systems need one or two barriers per structure
         __shared__ double2 sxy[EHIC_PRIOR_TILE];
         __shared__ double2 szr[EHIC_PRIOR_TILE];
+        __shared__ double sbox[EHIC_PRIOR_TILE / 32][6];
         const double rb2 = __dmul_rn(rb, rb);
         const double coarse = (rb + r_max) * (rb + r_max);
+        // this warp's own slice box, grown by the largest contact range (+ slack for the <= tests)
+        const double reach = 2.0 * r_max * (1.0 + 1e-12);
+        const double *bbk = bbox + ((long long)r * dm.S + k) * dm.n_slices * 6;
+        const int my_sl = min((int)((blockIdx.x * EHIC_PRIOR_THREADS + threadIdx.x) >> 5), dm.n_slices - 1);
+        const double mlo0 = bbk[my_sl * 6] - reach, mlo1 = bbk[my_sl * 6 + 1] - reach, mlo2 = bbk[my_sl * 6 + 2] - reach;
+        const double mhi0 = bbk[my_sl * 6 + 3] + reach, mhi1 = bbk[my_sl * 6 + 4] + reach, mhi2 = bbk[my_sl * 6 + 5] + reach;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
         for (int t0 = 0; t0 < dm.N; t0 += EHIC_PRIOR_TILE) {
             __syncthreads();
@@ -257,6 +296,10 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
                 sxy[q] = make_double2(xk[oo], xk[Np + oo]);
                 szr[q] = make_double2(xk[2 * Np + oo], dm.radii[oo]);
             }
+            for (int q = threadIdx.x; q < (EHIC_PRIOR_TILE / 32) * 6; q += EHIC_PRIOR_THREADS) {
+                const int psl = min(t0 / 32 + q / 6, dm.n_slices - 1);
+                sbox[q / 6][q % 6] = bbk[psl * 6 + q % 6];
+            }
             __syncthreads();
             const int cnt = min(EHIC_PRIOR_TILE, dm.N - t0);
             if (!EXACT) {
@@ -264,6 +307,10 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
                 // 32 partners per bit mask); the few partners within the coarse contact range are
                 // then evaluated from the mask, in ascending order
                 for (int q0 = 0; q0 < cnt; q0 += 32) {
+                    {   // warp-uniform: partner slice entirely out of reach of this warp's slice?
+                        const double *pb = sbox[q0 >> 5];
+                        if (pb[0] > mhi0 || pb[3] < mlo0 || pb[1] > mhi1 || pb[4] < mlo1 || pb[2] > mhi2 || pb[5] < mlo2) continue;
+                    }
                     unsigned hits = 0u;
 #pragma unroll
                     for (int qq = 0; qq < 32; qq++) {
@@ -295,6 +342,10 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
             }
 #pragma unroll 4
             for (int q = 0; EXACT && q < cnt; q++) {
+                if ((q & 31) == 0) {   // skipping a slice pair that cannot touch changes neither the terms nor their order
+                    const double *pb = sbox[q >> 5];
+                    if (pb[0] > mhi0 || pb[3] < mlo0 || pb[1] > mhi1 || pb[4] < mlo1 || pb[2] > mhi2 || pb[5] < mlo2) { q += 31; continue; }
+                }
                 const double2 pxy = sxy[q], pzr = szr[q];
                 const int o = t0 + q;
                 if (EXACT) {
@@ -779,6 +830,7 @@ struct BackwardTileArgs {
     const double *xs, *tw, *beta;
     double *Grow, *P;
     const unsigned char *tile_clean;   // [n_tiles]
+    const double *bbox;                // [R*S][n_slices][6] slice bounding boxes (NB only)
     int n_kg, nb;                      // structure groups per row block; fuse the nonbonded term
     double r_max;
 };
@@ -896,7 +948,22 @@ backward_tile_kernel(DevModel dm, TileDev td, BackwardTileArgs ba)
     double cx = 0.0, cy = 0.0, cz = 0.0, cr = 0.0;
     unsigned m[4] = {0u, 0u, 0u, 0u};
     int col0 = 0;
-    bool clean = false;
+    bool clean = false, nb_tile = false;
+    // bounding box of this warp's 128 row beads, grown by the largest contact range: column slices
+    // whose box lies outside cannot hold a nonbonded contact, their tiles skip the test altogether
+    double rlo0 = 0.0, rlo1 = 0.0, rlo2 = 0.0, rhi0 = 0.0, rhi1 = 0.0, rhi2 = 0.0;
+    const double *bbk = NB ? ba.bbox + rk * td.n_sl * 6 : nullptr;
+    if (NB) {
+        const double reach = 2.0 * ba.r_max * (1.0 + 1e-12);
+        const int s0 = 4 * I, s1 = min(4 * I + 3, td.n_sl - 1);
+        rlo0 = bbk[s0 * 6]; rlo1 = bbk[s0 * 6 + 1]; rlo2 = bbk[s0 * 6 + 2];
+        rhi0 = bbk[s0 * 6 + 3]; rhi1 = bbk[s0 * 6 + 4]; rhi2 = bbk[s0 * 6 + 5];
+        for (int q = s0 + 1; q <= s1; q++) {
+            rlo0 = fmin(rlo0, bbk[q * 6]); rlo1 = fmin(rlo1, bbk[q * 6 + 1]); rlo2 = fmin(rlo2, bbk[q * 6 + 2]);
+            rhi0 = fmax(rhi0, bbk[q * 6 + 3]); rhi1 = fmax(rhi1, bbk[q * 6 + 4]); rhi2 = fmax(rhi2, bbk[q * 6 + 5]);
+        }
+        rlo0 -= reach; rlo1 -= reach; rlo2 -= reach; rhi0 += reach; rhi1 += reach; rhi2 += reach;
+    }
     for (int c = 0; c < n_chunks; c++) {
         __pipeline_wait_prior(EHIC_BT_STAGES - 2);
         __syncthreads();
@@ -907,7 +974,11 @@ backward_tile_kernel(DevModel dm, TileDev td, BackwardTileArgs ba)
             col0 = 32 * td.tile_B[t];
             const int oc = min(col0 + lane, dm.N - 1);
             cx = xk[oc]; cy = xk[Np + oc]; cz = xk[2 * Np + oc];
-            if (NB) cr = dm.radii[oc];
+            if (NB) {
+                cr = dm.radii[oc];
+                const double *pb = bbk + td.tile_B[t] * 6;
+                nb_tile = !(pb[0] > rhi0 || pb[3] < rlo0 || pb[1] > rhi1 || pb[4] < rlo1 || pb[2] > rhi2 || pb[5] < rlo2);
+            }
             clean = ba.tile_clean[t] != 0;
             if (!clean) {
 #pragma unroll
@@ -916,8 +987,13 @@ backward_tile_kernel(DevModel dm, TileDev td, BackwardTileArgs ba)
         }
         const double *sd = smem + (c % EHIC_BT_STAGES) * 2048 + lane;
         double rx[8], ry[8], rz[8];
-        if (clean) backward_chunk<false, NB>(dm, sd, qg, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
-        else backward_chunk<true, NB>(dm, sd, qg, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
+        if (NB && nb_tile) {
+            if (clean) backward_chunk<false, true>(dm, sd, qg, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
+            else backward_chunk<true, true>(dm, sd, qg, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
+        } else {
+            if (clean) backward_chunk<false, false>(dm, sd, qg, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
+            else backward_chunk<true, false>(dm, sd, qg, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
+        }
         reduce8(rx, lane); reduce8(ry, lane); reduce8(rz, lane);
         if ((lane & 3) == 0 && k_ok) {
             const int col = col0 + qg * 8 + (((lane >> 2) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 4) & 1));
