@@ -325,7 +325,8 @@ def run_b200(args):
         peaks, peaks_kind = measured_peaks()
         fp64_tf, _ = engine.fma_peak(True, 10, local)
         fp32_tf, _ = engine.fma_peak(False, 10, local)
-        # dominant kernel: gather (likelihood gradient); algorithmic flop = 23 per (structure, data point)
+        # dominant kernel: the likelihood-gradient kernel (timing class "gather": backward_tile_kernel on the
+        # dense tile path, gather_kernel on the row path); algorithmic flop = 23 per (structure, data point)
         gather_ms = kern.get("gather", None) if kern else None
         flop_gather = FLOP_BWD_PER_PAIR * S * M * R
         ach = flop_gather / (gather_ms * 1e-3) / 1e12 if gather_ms else None
@@ -336,7 +337,8 @@ def run_b200(args):
         if os.path.exists(pj):
             with open(pj) as f:
                 prof = json.load(f)
-        roofline = {"bound": "fp64", "kernel": "gather_kernel", "achieved": ach, "peak": fp64_tf, "unit": "TFLOP/s",
+        tiles = model.info()["kt"] >= 10000
+        roofline = {"bound": "fp64", "kernel": "backward_tile_kernel" if tiles else "gather_kernel", "achieved": ach, "peak": fp64_tf, "unit": "TFLOP/s",
                     "frac": (ach / fp64_tf) if ach else None, "traffic": prof.get("gather_dram_bytes_per_launch"),
                     "peak_source": "measured here: DFMA issue-rate micro-benchmark (ehic_fma_peak); FP64/FP32 "
                                    "non-tensor peaks are not in MEASURED_PEAKS.json (SURVEY 8d)",
