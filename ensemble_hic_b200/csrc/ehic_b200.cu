@@ -322,10 +322,10 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         }
         // both tile kernels use more than the 48 KB of static shared memory
         cudaError_t e1 = cudaFuncSetAttribute(backward_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)(EHIC_BT_STAGES * 2048 * sizeof(double)));
+                                              (int)((EHIC_BT_STAGES * 2048 * sizeof(double) + 64)));
         if (e1 == cudaSuccess)
             e1 = cudaFuncSetAttribute(backward_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(EHIC_BT_STAGES * 2048 * sizeof(double)));
+                                      (int)((EHIC_BT_STAGES * 2048 * sizeof(double) + 64)));
         cudaError_t e2 = cudaSuccess;
         const int fsm = (int)forward_tile_smem(m->kt);
         switch (m->kt) {
@@ -513,7 +513,7 @@ static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_
                 LAUNCHED();
             }
             const unsigned blocks = (unsigned)((long long)R * m->td.n_rb * ba.n_kg);
-            const size_t sm = EHIC_BT_STAGES * 2048 * sizeof(double);
+            const size_t sm = (EHIC_BT_STAGES * 2048 * sizeof(double) + 64);
             if (ga.nb_fused) backward_tile_kernel<true><<<blocks, 128, sm, st>>>(m->dm, m->td, ba);
             else backward_tile_kernel<false><<<blocks, 128, sm, st>>>(m->dm, m->td, ba);
             LAUNCHED();

@@ -62,6 +62,40 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // ---------------------------------------------------------------------------------------
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: one elected thread moves a
+// whole contiguous stage (up to 16 KB) global -> shared instead of hundreds of per-thread cp.async.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
 // x[R][S][N][3] -> xs[R][S][3][Np]  and  xt[R][nkt][Np][KT][3]
 //
 // xt ("tile-AoS") is the gather kernel's copy: one record holds bead o of the KT structures of
@@ -930,17 +964,24 @@ backward_tile_kernel(DevModel dm, TileDev td, BackwardTileArgs ba)
     double *Pk = ba.P + (rk * td.n_rb + I) * (long long)dm.N * 3;
     const int t0 = td.rb_begin[I], n_tiles = td.rb_begin[I + 1] - t0;
     const int n_chunks = n_tiles * 4;
+    // stage ring filled by TMA bulk copies: thread 0 arms the stage's mbarrier with the byte count and
+    // issues two 8 KB copies (contact distances, weights); everybody waits on the barrier's phase
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem + EHIC_BT_STAGES * 2048);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < EHIC_BT_STAGES; q++) mbar_init(&full[q], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
     auto issue = [&](int c) {
-        if (c < n_chunks) {
+        if (c < n_chunks && threadIdx.x == 0) {
             const int st = c % EHIC_BT_STAGES;
             const long long base = (long long)(t0 + (c >> 2)) * 4096 + (c & 3) * 1024;
             double *d0 = smem + st * 2048;
-            for (int q = threadIdx.x; q < 512; q += 128) {
-                __pipeline_memcpy_async(&d0[q * 2], td.dc + base + q * 2, 16);
-                __pipeline_memcpy_async(&d0[1024 + q * 2], twr + base + q * 2, 16);
-            }
+            mbar_expect_tx(&full[st], 2 * 1024 * (unsigned)sizeof(double));
+            bulk_g2s(d0, td.dc + base, 1024 * (unsigned)sizeof(double), &full[st]);
+            bulk_g2s(d0 + 1024, twr + base, 1024 * (unsigned)sizeof(double), &full[st]);
         }
-        __pipeline_commit();
     };
 #pragma unroll
     for (int c = 0; c < EHIC_BT_STAGES - 1; c++) issue(c);
@@ -965,8 +1006,8 @@ backward_tile_kernel(DevModel dm, TileDev td, BackwardTileArgs ba)
         rlo0 -= reach; rlo1 -= reach; rlo2 -= reach; rhi0 += reach; rhi1 += reach; rhi2 += reach;
     }
     for (int c = 0; c < n_chunks; c++) {
-        __pipeline_wait_prior(EHIC_BT_STAGES - 2);
-        __syncthreads();
+        mbar_wait(&full[c % EHIC_BT_STAGES], (unsigned)((c / EHIC_BT_STAGES) & 1));
+        __syncthreads();                                  // everyone is done with chunk c-1: its stage may be refilled
         issue(c + EHIC_BT_STAGES - 1);
         const int qg = c & 3;
         if (qg == 0) {                                   // new tile: column beads (one per lane) and masks
@@ -1000,7 +1041,6 @@ backward_tile_kernel(DevModel dm, TileDev td, BackwardTileArgs ba)
             if (col < dm.N) { double *o = Pk + (long long)col * 3; o[0] = rx[0]; o[1] = ry[0]; o[2] = rz[0]; }
         }
     }
-    __pipeline_wait_prior(0);
     if (k_ok) {
 #pragma unroll
         for (int rb = 0; rb < 4; rb++) {
