@@ -101,7 +101,7 @@ KernelTimer::~KernelTimer() { if (idx >= 0) cudaEventRecord(m->timed[idx].b, st)
 
 static size_t forward_tile_smem(int kt)
 {
-    return sizeof(double) * (4096 + (size_t)EHIC_FT_STAGES * (128 + 32) * kt * 3);
+    return sizeof(double) * (4096 + (size_t)EHIC_FT_STAGES * (128 + 32) * kt * 3) + 64;   // + mbarriers
 }
 
 template <typename T>

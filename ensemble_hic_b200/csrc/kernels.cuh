@@ -717,31 +717,42 @@ forward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xt, cons
     const double alpha = dm.alpha;
     const int n_row = min(128, Np - row0);             // row records that exist in xt
 
-    // contact distances of the whole tile: 32 KB, once
-    for (int q = threadIdx.x; q < 2048; q += 256)
-        __pipeline_memcpy_async(&s_dc[q * 2], td.dc + (long long)tile * 4096 + q * 2, 16);
+    // TMA bulk copies completing on mbarriers: full[st] for the per-structure-tile records,
+    // full[STAGES] for the tile's contact distances (32 KB, once)
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(s_col + EHIC_FT_STAGES * 32 * REC);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q <= EHIC_FT_STAGES; q++) mbar_init(&full[q], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&full[EHIC_FT_STAGES], 4096 * (unsigned)sizeof(double));
+        bulk_g2s(s_dc, td.dc + (long long)tile * 4096, 16384, &full[EHIC_FT_STAGES]);
+        bulk_g2s(s_dc + 2048, td.dc + (long long)tile * 4096 + 2048, 16384, &full[EHIC_FT_STAGES]);
+    }
     auto issue = [&](int kt) {
-        if (kt < nkt) {
+        if (kt < nkt && threadIdx.x == 0) {
             const int st = kt % EHIC_FT_STAGES;
             const double *src_row = recs + ((long long)kt * Np + row0) * REC;
             const double *src_col = recs + ((long long)kt * Np + col0) * REC;
-            for (int q = threadIdx.x; q < n_row * REC / 2; q += 256)
-                __pipeline_memcpy_async(&s_row[st * 128 * REC + q * 2], src_row + q * 2, 16);
-            for (int q = threadIdx.x; q < 32 * REC / 2; q += 256)
-                __pipeline_memcpy_async(&s_col[st * 32 * REC + q * 2], src_col + q * 2, 16);
+            const unsigned row_bytes = (unsigned)(n_row * REC * sizeof(double)), col_bytes = (unsigned)(32 * REC * sizeof(double));
+            mbar_expect_tx(&full[st], row_bytes + col_bytes);
+            bulk_g2s(&s_row[st * 128 * REC], src_row, row_bytes, &full[st]);
+            bulk_g2s(&s_col[st * 32 * REC], src_col, col_bytes, &full[st]);
         }
-        __pipeline_commit();
     };
 #pragma unroll
     for (int c = 0; c < EHIC_FT_STAGES - 1; c++) issue(c);
+    mbar_wait(&full[EHIC_FT_STAGES], 0u);
 
     double acc[QC];
 #pragma unroll
     for (int q = 0; q < QC; q++) acc[q] = 0.0;
     const int nfull = dm.S / KT;
     for (int kt = 0; kt < nkt; kt++) {
-        __pipeline_wait_prior(EHIC_FT_STAGES - 2);
-        __syncthreads();
+        mbar_wait(&full[kt % EHIC_FT_STAGES], (unsigned)((kt / EHIC_FT_STAGES) & 1));
+        __syncthreads();                                  // structure tile kt-1 is consumed: its stage may be refilled
         issue(kt + EHIC_FT_STAGES - 1);
         if (!warp_live) continue;
         const int st = kt % EHIC_FT_STAGES;
@@ -788,8 +799,6 @@ forward_tile_kernel(DevModel dm, TileDev td, const double *__restrict__ xt, cons
             }
         }
     }
-    __pipeline_wait_prior(0);
-
     double term = 0.0;
     const double nrm = norm[r];
     const double lam = lammda ? lammda[r] : 1.0;       // the backward tile kernel consumes lammda * w
