@@ -535,6 +535,7 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
     __shared__ __align__(16) int s_o[EHIC_STAGES][EHIC_CHUNK * 32];
     __shared__ __align__(16) double s_dc[EHIC_STAGES][EHIC_CHUNK * 32];
     __shared__ __align__(16) double s_w[EHIC_STAGES][EHIC_CHUNK * 32];
+    __shared__ __align__(8) unsigned long long full[EHIC_STAGES];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ktg = blockIdx.x % nktg;
@@ -575,25 +576,29 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
         const double *gw = ga.wbuf + (long long)r * dm.wstride + off;
         const double alpha = dm.alpha;
         const double aa = __dmul_rn(alpha, alpha);
-        // one chunk = 16 entries x 32 lanes: 2 KB of partner indices + 4 KB + 4 KB of doubles,
-        // moved as 640 16-byte cp.async copies spread over the CTA's threads
+        // one chunk = 16 entries x 32 lanes: 2 KB of partner indices + 4 KB + 4 KB of doubles, moved by
+        // three TMA bulk copies issued by thread 0 and completing on the stage's mbarrier
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int q = 0; q < EHIC_STAGES; q++) mbar_init(&full[q], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
         auto issue = [&](int c) {
-            if (c < nchunks) {
+            if (c < nchunks && threadIdx.x == 0) {
                 const int st = c % EHIC_STAGES;
                 const long long base = (long long)c * EHIC_CHUNK * 32;
-                for (int q = threadIdx.x; q < 640; q += blockDim.x) {
-                    if (q < 128) __pipeline_memcpy_async(&s_o[st][q * 4], gj + base + q * 4, 16);
-                    else if (q < 384) __pipeline_memcpy_async(&s_dc[st][(q - 128) * 2], gdc + base + (q - 128) * 2, 16);
-                    else __pipeline_memcpy_async(&s_w[st][(q - 384) * 2], gw + base + (q - 384) * 2, 16);
-                }
+                mbar_expect_tx(&full[st], EHIC_CHUNK * 32 * 20u);
+                bulk_g2s(&s_o[st][0], gj + base, EHIC_CHUNK * 32 * 4u, &full[st]);
+                bulk_g2s(&s_dc[st][0], gdc + base, EHIC_CHUNK * 32 * 8u, &full[st]);
+                bulk_g2s(&s_w[st][0], gw + base, EHIC_CHUNK * 32 * 8u, &full[st]);
             }
-            __pipeline_commit();
         };
 #pragma unroll
         for (int c = 0; c < EHIC_STAGES - 1; c++) issue(c);
         for (int c = 0; c < nchunks; c++) {
-            __pipeline_wait_prior(EHIC_STAGES - 2);
-            __syncthreads();                       // chunk c visible; everyone is done with chunk c-1
+            mbar_wait(&full[c % EHIC_STAGES], (unsigned)((c / EHIC_STAGES) & 1));
+            __syncthreads();                       // everyone is done with chunk c-1: its stage may be refilled
             issue(c + EHIC_STAGES - 1);
             const int st = c % EHIC_STAGES;
             const int cnt = min(EHIC_CHUNK, width - c * EHIC_CHUNK);
@@ -633,7 +638,6 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
                 }
             }
         }
-        __pipeline_wait_prior(0);
     }
 
     // ---- epilogue -------------------------------------------------------------------------
