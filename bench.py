@@ -104,6 +104,18 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bench_config(world):
+    """the `config` object shared by both arms (own and --impl reference)"""
+    M = N_BEADS * (N_BEADS - 1) // 2 - (N_BEADS - 1)
+    R = REPLICAS_PER_GPU
+    return {"workload": "D: synthetic chain %d beads x %d structures, dense contact list M=%d, %d replicas per GPU "
+                        "(%d total), posterior gradient (likelihood+nonbonded+backbone)" % (N_BEADS, N_STRUCT, M, R, R * world),
+            "replicas_per_gpu": R, "n_beads": N_BEADS, "n_structures": N_STRUCT, "n_data": M,
+            "coordinates": "seeded random-walk chains, step 1.8 r (SURVEY 8d ii)",
+            "l2": "working set per step (contact tiles 43 MB + weights 17 MB/replica + coordinates + reaction partials "
+                  "77 MB/replica) exceeds the 126 MB L2; no explicit flush"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -185,8 +197,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "D: synthetic chain 2000 beads x 100 structures, dense contact list M=1997001, "
-                                   "posterior gradient (likelihood+nonbonded+backbone)"},
+            "config": bench_config(args.gpus),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -359,12 +370,7 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "D: synthetic chain 2000 beads x 100 structures, dense contact list M=%d, "
-                                       "%d replicas per GPU (%d total), posterior gradient "
-                                       "(likelihood+nonbonded+backbone)" % (M, R, n_total),
-                           "replicas_per_gpu": R, "n_beads": N, "n_structures": S, "n_data": M,
-                           "l2": "working set per step (contact rows 96 MB + weights 32 MB/replica + coordinates) "
-                                 "exceeds the 126 MB L2; no explicit flush"},
+                "config": bench_config(world),
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_x + 3 * R * 8,
                         "d2h_bytes_per_step": bytes_x,
