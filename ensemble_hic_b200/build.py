@@ -31,16 +31,27 @@ def nvcc_path():
 
 
 def build(force=False, verbose=False):
-    """Compile the library if needed; returns its path."""
+    """Compile the library if needed; returns its path.  Safe when several ranks start at once:
+    the build runs under an exclusive file lock into a temporary file that is renamed into place."""
     if not force and not _stale():
         return LIB
+    import fcntl
     nvcc = nvcc_path()
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libehic_b200.so (there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, "ehic_b200.cu"), "-o", LIB]
-    if verbose:
-        print("[ensemble_hic_b200]", " ".join(cmd))
-    subprocess.check_call(cmd, cwd=CSRC)
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():        # another process built it while we waited
+                return LIB
+            tmp = LIB + ".tmp.%d" % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, "ehic_b200.cu"), "-o", tmp]
+            if verbose:
+                print("[ensemble_hic_b200]", " ".join(cmd))
+            subprocess.check_call(cmd, cwd=CSRC)
+            os.replace(tmp, LIB)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
