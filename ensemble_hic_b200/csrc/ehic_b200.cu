@@ -572,6 +572,7 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     if (!d_x) return fail(EHIC_ERR_INVALID, "null coordinates");
     terms &= EHIC_TERM_ALL;
     if (!m->dm.sphere_active) terms &= ~EHIC_TERM_SPHERE;
+    if (m->dm.M == 0) terms &= ~EHIC_TERM_LIKELIHOOD;         // no data points: the likelihood term is vacuous
     const bool lik = (terms & EHIC_TERM_LIKELIHOOD) != 0;
     const int prior_terms = terms & ~EHIC_TERM_LIKELIHOOD;
     if ((lik || d_md) && !d_norm) return fail(EHIC_ERR_INVALID, "norm required for the likelihood term");

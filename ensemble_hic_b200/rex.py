@@ -114,7 +114,8 @@ class ReplicaExchange(object):
     """
 
     def __init__(self, backend, schedule, x0, norm0, hmc, norm_prior=None, counts_sum=0.0,
-                 output_folder=None, seed=0, rank=0, world_size=1, dist=None, momenta="numpy"):
+                 output_folder=None, seed=0, rank=0, world_size=1, dist=None, momenta="numpy",
+                 stats_folder=None):
         self.be = backend
         self.lam_T = np.asarray(schedule["lammda"], dtype=np.float64)
         self.bet_T = np.asarray(schedule["beta"], dtype=np.float64)
@@ -130,13 +131,17 @@ class ReplicaExchange(object):
         self.adaption_limit = int(hmc.get("adaption_limit", 0))
         self.up, self.down = float(hmc.get("adaption_uprate", 1.05)), float(hmc.get("adaption_downrate", 0.95))
         # per-TEMPERATURE quantities (identical on every rank)
-        self.timestep_T = np.full(self.T, float(hmc["timestep"]))
+        ts = np.asarray(hmc["timestep"], dtype=np.float64)      # scalar, or one timestep per temperature (continuation)
+        self.timestep_T = np.full(self.T, float(ts)) if ts.ndim == 0 else ts.astype(np.float64).copy()
+        assert len(self.timestep_T) == self.T
         self.n_acc_T = np.zeros(self.T); self.n_hmc_T = np.zeros(self.T)
         self.re_acc = np.zeros(max(self.T - 1, 1)); self.re_try = np.zeros(max(self.T - 1, 1))
         self.temp_of_slot = np.arange(self.T)
         self.slot_of_temp = np.arange(self.T)
         self.norm_prior, self.counts_sum = norm_prior, float(counts_sum)
         self.out = output_folder
+        self.stats_out = stats_folder if stats_folder is not None else (
+            None if output_folder is None else os.path.join(output_folder, "statistics"))
         self.momenta = momenta
         self.rng_swap = np.random.RandomState(seed)                       # shared by all ranks
         self.rng_slot = [np.random.RandomState(seed + 1 + s) for s in range(self.lo, self.hi)]
@@ -263,10 +268,10 @@ class ReplicaExchange(object):
         row = [str(self.step)]
         for t in range(self.T):
             row += ["%.6f" % p_acc[t], "%.6e" % self.timestep_T[t]]
-        with open(os.path.join(self.out, "statistics", "mcmc_stats.txt"), "a") as f:
+        with open(os.path.join(self.stats_out, "mcmc_stats.txt"), "a") as f:
             f.write("\t".join(row) + "\n")
         re_rate = self.re_acc / np.maximum(self.re_try, 1)
-        with open(os.path.join(self.out, "statistics", "re_stats.txt"), "a") as f:
+        with open(os.path.join(self.stats_out, "re_stats.txt"), "a") as f:
             f.write("\t".join([str(self.step)] + ["%.6f" % v for v in re_rate[:max(self.T - 1, 0)]]) + "\n")
         if self.works:
             with open(os.path.join(self.out, "works", "works_%d.pickle" % self.step), "wb") as f:
@@ -324,6 +329,38 @@ class ExchangeMaster(object):
 
     def terminate_replicas(self):
         pass
+
+
+def load_continuation(output_folder, n_replicas, dump_interval, n_cont=1):
+    """What scripts/continue_simulation/setup_continue.py extracts from a finished run: the offset
+    (first sample index without a dump file), the last dumped state of every temperature, and the
+    HMC timesteps from the last row of mcmc_stats.txt (columns 2::2).  Also writes the reference's
+    artefacts init_states.npy / init_norms.npy / timesteps.npy into init_continue{n_cont}/."""
+    out = output_folder if output_folder.endswith("/") else output_folder + "/"
+    fname = out + "samples/samples_replica{}_{}-{}.pickle"
+    offset = 0
+    while os.path.exists(fname.format(1, offset, offset + dump_interval)):
+        offset += dump_interval
+    if offset == 0:
+        raise IOError("no dumped samples under %ssamples/: nothing to continue from" % out)
+    states = []
+    for t in range(1, n_replicas + 1):
+        with open(fname.format(t, offset - dump_interval, offset), "rb") as f:
+            states.append(pickle.load(f)[-1])
+    structures = np.array([s.variables["structures"] for s in states])
+    norms = np.array([s.variables["norm"] for s in states]) if "norm" in states[0].variables else None
+    stats_dir = out + ("statistics/" if n_cont == 1 else "init_continue%d/statistics/" % (n_cont - 1))
+    timesteps = None
+    if os.path.exists(stats_dir + "mcmc_stats.txt"):
+        timesteps = np.atleast_2d(np.loadtxt(stats_dir + "mcmc_stats.txt"))[-1, 2::2]
+    cont = out + "init_continue%d/" % n_cont
+    os.makedirs(cont + "statistics", exist_ok=True)
+    np.save(cont + "init_states.npy", structures)
+    if norms is not None:
+        np.save(cont + "init_norms.npy", norms)
+    if timesteps is not None:
+        np.save(cont + "timesteps.npy", timesteps)
+    return dict(offset=offset, structures=structures, norms=norms, timesteps=timesteps, cont_folder=cont)
 
 
 def copy_run_metadata(config_file, schedule, output_folder):

@@ -22,7 +22,7 @@ import numpy as np
 def main(argv=None):
     import torch
     from . import setup_functions as sf
-    from .rex import EngineBackend, ReplicaExchange, copy_run_metadata, partition
+    from .rex import EngineBackend, ReplicaExchange, copy_run_metadata, load_continuation, partition
 
     ap = argparse.ArgumentParser()
     ap.add_argument("config")
@@ -31,6 +31,9 @@ def main(argv=None):
     ap.add_argument("--n-samples", type=int, default=None, help="override [replica] n_samples")
     ap.add_argument("--momenta", default="numpy", choices=["numpy", "torch"])
     ap.add_argument("--quiet", action="store_true")
+    ap.add_argument("--continue", dest="n_cont", type=int, default=0, metavar="N",
+                    help="continue a finished run (N-th continuation): start from the last dumped states and "
+                         "timesteps, like scripts/continue_simulation of the reference")
     args = ap.parse_args(argv)
 
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
@@ -66,23 +69,41 @@ def main(argv=None):
         prior = posterior.priors["norm_prior"]
         norm_prior = (prior["shape"].value, prior["rate"].value)
     else:
-        norm0 = float(posterior["norm"].value)
+        # run_simulation.py:93-94: a norm that is not sampled is fixed at max(count) / n_structures
+        norm0 = float(np.max(counts)) / float(settings["general"]["n_structures"])
+        posterior["norm"].set(norm0)
         norm_prior = None
-    if rank == 0:
+    hmc = dict(timestep=float(settings["structures_hmc"]["timestep"]),
+               trajectory_length=int(settings["structures_hmc"]["trajectory_length"]),
+               adaption_limit=int(settings["structures_hmc"]["adaption_limit"]))
+    offset, stats_folder = 0, None
+    if args.n_cont > 0:
+        # every rank reads the same files; rank 0 also writes init_states.npy etc.
+        if rank == 0:
+            cont = load_continuation(out, T, int(re_params["samples_dump_interval"]), args.n_cont)
+        if dist is not None:
+            dist.barrier()
+        if rank != 0:
+            cont = load_continuation(out, T, int(re_params["samples_dump_interval"]), args.n_cont)
+        offset, stats_folder = cont["offset"], cont["cont_folder"] + "statistics"
+        x0 = cont["structures"][bounds[rank]:bounds[rank + 1]]
+        if cont["norms"] is not None and sample_norm:
+            norm0 = cont["norms"][bounds[rank]:bounds[rank + 1]]
+        if cont["timesteps"] is not None:
+            hmc["timestep"] = cont["timesteps"]
+    elif rank == 0:
         master = sf.setup_default_re_master(T, out)
         copy_run_metadata(args.config, schedule, out)
     if dist is not None:
         dist.barrier()
-    hmc = dict(timestep=float(settings["structures_hmc"]["timestep"]),
-               trajectory_length=int(settings["structures_hmc"]["trajectory_length"]),
-               adaption_limit=int(settings["structures_hmc"]["adaption_limit"]))
     rex = ReplicaExchange(EngineBackend(posterior.engine), schedule, x0, norm0, hmc, norm_prior=norm_prior,
-                          counts_sum=float(counts.sum()), output_folder=out, seed=args.seed, rank=rank,
-                          world_size=world, dist=dist, momenta=args.momenta)
+                          counts_sum=float(counts.sum()), output_folder=out, seed=args.seed + 104729 * args.n_cont,
+                          rank=rank, world_size=world, dist=dist, momenta=args.momenta, stats_folder=stats_folder)
     n = (args.n_samples if args.n_samples is not None else int(re_params["n_samples"])) + 1
     rex.run(n, swap_interval=int(re_params["swap_interval"]), status_interval=int(re_params["print_status_interval"]),
             dump_interval=int(re_params["samples_dump_interval"]), dump_step=int(re_params["samples_dump_step"]),
-            statistics_update_interval=int(re_params["statistics_update_interval"]), verbose=not args.quiet)
+            statistics_update_interval=int(re_params["statistics_update_interval"]), offset=offset,
+            verbose=not args.quiet)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -237,3 +237,62 @@ def test_nblist_and_forcefield_objects(co):
     forces = np.zeros((150, 3))
     E = ff.isd_ff.update_gradient(x, forces)
     assert relerr(forces.ravel(), oracle.gradient(x)) < TOL and E == pytest.approx(oracle.energy(x), rel=1e-12)
+
+
+def test_run_simulation_and_continuation_single_gpu(hairpin, tmp_path):
+    """the launcher end to end on one GPU: output layout of the reference, then a continuation"""
+    import glob
+    import pickle
+    from ensemble_hic_b200 import run_simulation
+    cfg, g = hairpin
+    txt = open(cfg).read().replace("n_replicas = 2", "n_replicas = 4").replace("samples_dump_interval = 100", "samples_dump_interval = 20") \
+                          .replace("samples_dump_step = 20", "samples_dump_step = 5").replace("statistics_update_interval = 40", "statistics_update_interval = 10") \
+                          .replace("timestep = 1e-4", "timestep = 1e-3")
+    open(cfg, "w").write(txt)
+    rex = run_simulation.main([cfg, "--n-samples", "60", "--quiet", "--seed", "3"])
+    out = str(tmp_path / "out") + "/"
+    assert os.path.exists(out + "config.cfg") and os.path.exists(out + "schedule.pickle")
+    sched = pickle.load(open(out + "schedule.pickle", "rb"))
+    assert np.allclose(sched["lammda"], np.linspace(0, 1, 4)) and np.allclose(sched["beta"], np.linspace(0.001, 1, 4))
+    files = sorted(os.path.basename(f) for f in glob.glob(out + "samples/*.pickle"))
+    assert files == sorted("samples_replica%d_%d-%d.pickle" % (t, a, a + 20) for t in range(1, 5) for a in (0, 20, 40))
+    states = pickle.load(open(out + "samples/samples_replica4_40-60.pickle", "rb"))
+    assert len(states) == 4 and states[-1].variables["structures"].shape == (2 * 23 * 3,) and states[-1].variables["norm"] > 0
+    stats = np.loadtxt(out + "statistics/mcmc_stats.txt")
+    assert stats.shape[1] == 9 and stats[-1, 0] == 60
+    assert sorted(rex.temp_of_slot.tolist()) == [0, 1, 2, 3] and rex.n_hmc_T.sum() > 0
+    # continuation: starts at offset 60 from the dumped states and timesteps
+    rex2 = run_simulation.main([cfg, "--n-samples", "40", "--quiet", "--continue", "1"])
+    assert rex2.step == 60 + 40
+    assert os.path.exists(out + "init_continue1/init_states.npy") and os.path.exists(out + "init_continue1/timesteps.npy")
+    assert np.allclose(np.load(out + "init_continue1/timesteps.npy"), stats[-1, 2::2])
+    assert os.path.exists(out + "samples/samples_replica1_60-80.pickle") and os.path.exists(out + "samples/samples_replica3_80-100.pickle")
+    assert os.path.exists(out + "init_continue1/statistics/mcmc_stats.txt")
+    first = pickle.load(open(out + "samples/samples_replica2_60-80.pickle", "rb"))[0]
+    assert np.isfinite(first.variables["structures"]).all()
+
+
+def test_api_errors():
+    from ensemble_hic_b200 import _lib
+    from ensemble_hic_b200.engine import Model
+    pb = make_problem(seed=1, S=2, N=20)
+    m = Model(2, pb["radii"], pb["data"], pb["cds"], alpha=10.0, max_replicas=2)
+    X3 = np.stack([pb["X"]] * 3)
+    with pytest.raises(_lib.EhicError) as e:
+        m.evaluate(X3, 1.0)                                   # 3 replicas > max_replicas
+    assert e.value.code == _lib.ERR_INVALID
+    with pytest.raises(ValueError):
+        m.evaluate(pb["X"].ravel()[:-3], 1.0)                 # not a multiple of S*N*3
+    with pytest.raises(_lib.EhicError):
+        m.evaluate(pb["X"], None)                             # likelihood term needs norm
+    with pytest.raises(_lib.EhicError) as e:
+        Model(2, pb["radii"], np.array([[0, 25, 1]]), np.array([1.0]))      # bead index out of range
+    assert "outside" in str(e.value)
+    with pytest.raises(_lib.EhicError):
+        Model(2, pb["radii"], np.array([[3, 3, 1]]), np.array([1.0]))       # self pair
+    with pytest.raises(ValueError):
+        Model(2, pb["radii"], pb["data"], pb["cds"][:5])
+    empty = Model(2, pb["radii"])                              # no data: priors only
+    out = empty.evaluate(pb["X"], None, terms=_lib.TERM_ALL, energies=True)
+    assert out["energies"][0, 0] == 0.0 and np.isfinite(out["grad"]).all()
+    assert empty.mock_data(pb["X"], 1.0).shape == (1, 0)

@@ -59,3 +59,25 @@ def test_two_ranks_reproduce_one_rank(tmp_path):
         for sa, sb in zip(a, b):
             assert np.array_equal(sa.variables["structures"], sb.variables["structures"])
             assert sa.variables["norm"] == sb.variables["norm"]
+
+
+def test_continuation_artifacts(tmp_path):
+    """scripts/continue_simulation/setup_continue.py semantics: offset, last states, timesteps"""
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    from ensemble_hic_b200.rex import load_continuation
+    out = str(tmp_path / "w1")
+    one = _run(out, 1)[0]
+    c = load_continuation(out, 5, 10)
+    assert c["offset"] == 30
+    last = [pickle.load(open(os.path.join(out, "samples", "samples_replica%d_20-30.pickle" % t), "rb"))[-1] for t in range(1, 6)]
+    assert np.array_equal(c["structures"], np.array([s.variables["structures"] for s in last]))
+    assert np.array_equal(c["norms"], np.array([s.variables["norm"] for s in last]))
+    stats = np.loadtxt(os.path.join(out, "statistics", "mcmc_stats.txt"))
+    assert np.array_equal(c["timesteps"], stats[-1, 2::2]) and np.allclose(c["timesteps"], one["timestep_T"], rtol=1e-5)
+    for f in ("init_states.npy", "init_norms.npy", "timesteps.npy"):
+        assert os.path.exists(os.path.join(out, "init_continue1", f))
+    assert np.array_equal(np.load(os.path.join(out, "init_continue1", "init_states.npy")), c["structures"])
+    import pytest
+    with pytest.raises(IOError):
+        load_continuation(str(tmp_path / "nothing"), 5, 10)
