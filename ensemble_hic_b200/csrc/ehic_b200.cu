@@ -60,12 +60,15 @@ struct ehic_model {
     // workspace
     double *xs[2] = {nullptr, nullptr};   // SoA working copies (forward + prior kernels)
     double *xt[2] = {nullptr, nullptr};   // tile-AoS working copies (gather kernel)
-    double *wbuf = nullptr, *gprior = nullptr, *bbox = nullptr;
+    double *wbuf = nullptr, *gprior = nullptr, *bbox = nullptr, *partC = nullptr;
+    int *cell_list = nullptr;
+    bool use_cells = false;         // fast mode: nonbonded term through the per-structure cell grid
     double *partA = nullptr, *partP = nullptr, *partK = nullptr;
     double *energies = nullptr, *kinetic = nullptr;
     int nA = 0;                     // forward blocks per replica
     int nPx = 0;                    // prior blocks per structure
     int prior_threads = 256;
+    bool last_prior_used_cells = false;
     int cur_xt = 0;                 // which xt buffer matches the xs buffer handed to launch_forward
     int kt = 1, nkt = 1, nktg = 1;  // structures per warp, tiles per replica, tile groups (gw warps) per slice
     int gw = 4;                     // warps per gather CTA
@@ -191,8 +194,8 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         return fail(EHIC_ERR_INVALID, "data_points / contact_distances missing");
     if (!desc->bead_radii) return fail(EHIC_ERR_INVALID, "bead_radii missing");
     if (desc->max_replicas <= 0) return fail(EHIC_ERR_INVALID, "max_replicas must be positive");
-    if (desc->flags & (EHIC_FLAG_FP32 | EHIC_FLAG_NB_CELLS))
-        return fail(EHIC_ERR_INVALID, "EHIC_FLAG_FP32 / EHIC_FLAG_NB_CELLS are not available in this build");
+    if (desc->flags & EHIC_FLAG_FP32)
+        return fail(EHIC_ERR_INVALID, "EHIC_FLAG_FP32 is not available in this build (see DESIGN.md)");
     int rc = check_device(device);
     if (rc) return rc;
     CU(cudaSetDevice(device));
@@ -304,6 +307,17 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     DA(m->wbuf, Rm * (size_t)dm.wstride);
     DA(m->gprior, Rm * S * (size_t)N * 3);
     DA(m->bbox, Rm * S * (size_t)L.n_slices * 6);
+    DA(m->partC, Rm * S);
+    {
+        const char *nbm = getenv("EHIC_NB");
+        m->use_cells = !exact && (N >= 4096 || (nbm && !strcmp(nbm, "cells") && N >= 32)) && !(nbm && !strcmp(nbm, "pairs"));
+        if ((desc->flags & EHIC_FLAG_NB_CELLS) && !exact) m->use_cells = true;
+        if (m->use_cells) {
+            int *cl = nullptr;
+            if (cudaMalloc(&cl, sizeof(int) * Rm * S * (size_t)N) != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_NOMEM, "cudaMalloc failed"); }
+            m->owned.push_back(cl); m->cell_list = cl;
+        }
+    }
     DA(m->partA, Rm * (size_t)std::max(m->nA, 1));
     DA(m->partP, Rm * (size_t)S * m->nPx * 3);
     DA(m->partK, Rm * (size_t)L.n_slices * m->nktg * m->gw);
@@ -464,6 +478,10 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
     double *gp = want_grad ? m->gprior : nullptr, *pp = want_energy ? m->partP : nullptr;
     KernelTimer kt_(m, KC_PRIOR, st);
     const bool ex = (m->flags & EHIC_FLAG_EXACT) != 0;
+    // compact structures go through the cell grid, extended ones through the box-pruned all-pairs sweep;
+    // the two kernels take the same per-structure decision from the slice boxes
+    const bool cells = m->use_cells && (terms & EHIC_TERM_NONBONDED);
+    m->last_prior_used_cells = cells;
     if (terms & EHIC_TERM_NONBONDED) {
         dim3 gb((unsigned)m->dm.n_slices, (unsigned)((long long)R * m->dm.S));
         bbox_kernel<<<gb, 32, 0, st>>>(xs, m->bbox, m->dm.N, m->dm.Np, m->dm.n_slices);
@@ -471,8 +489,8 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
     }
 #define PK(T)                                                                                         \
     do {                                                                                              \
-        if (ex) prior_kernel<true, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max, m->bbox);   \
-        else prior_kernel<false, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max, m->bbox);     \
+        if (ex) prior_kernel<true, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max, m->bbox, 0);   \
+        else prior_kernel<false, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max, m->bbox, cells ? 1 : 0);     \
     } while (0)
     switch (m->prior_threads) {
     case 64: PK(64); break;
@@ -481,6 +499,12 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
     }
 #undef PK
     LAUNCHED();
+    if (cells) {
+        dim3 gc((unsigned)m->dm.S, (unsigned)R);
+        cell_nonbonded_kernel<<<gc, EHIC_CELL_THREADS, 0, st>>>(m->dm, xs, d_beta, gp, want_energy ? m->partC : nullptr,
+                                                               m->r_max, m->cell_list, m->bbox);
+        LAUNCHED();
+    }
     CU(cudaGetLastError());
     return EHIC_OK;
 }
@@ -541,6 +565,7 @@ static int launch_finalize(ehic_model *m, int R, bool haveA, bool haveP, bool ha
                                        haveP ? m->partP : nullptr, (long long)m->dm.S * m->nPx,
                                        haveK ? m->partK : nullptr,
                                        m->use_tiles ? (long long)m->dm.S * m->nKc : (long long)m->dm.n_slices * m->nktg * m->gw,
+                                       (haveP && m->last_prior_used_cells) ? m->partC : nullptr, m->dm.S,
                                        d_energies, d_kin);
     LAUNCHED();
     CU(cudaGetLastError());

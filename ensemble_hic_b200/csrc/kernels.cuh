@@ -289,12 +289,38 @@ bbox_kernel(const double *__restrict__ xs, double *__restrict__ bbox, int N, int
 // per-CTA energy partials partP[(r*S+k)*gridDim.x + blockIdx.x][3] = (sum a^4, sum bb, sum sph).
 #define EHIC_PRIOR_MAX_THREADS 256
 #define EHIC_PRIOR_TILE 512
+#define EHIC_CELL_MAX 4096
+
+// Structures are routed per evaluation: compact ones (grid of contact-range cells fits EHIC_CELL_MAX)
+// go to cell_nonbonded_kernel, extended ones to the box-pruned all-pairs sweep of prior_kernel.
+// Both kernels call this with the same slice boxes, so they always agree.  Executed by warp 0.
+__device__ __forceinline__ bool structure_fits_cells(const double *__restrict__ bbk, int n_slices, double r_max,
+                                                     int lane, double (&lo)[3], double (&hi)[3])
+{
+#pragma unroll
+    for (int c = 0; c < 3; c++) { lo[c] = 1e300; hi[c] = -1e300; }
+    for (int q = lane; q < n_slices; q += 32)
+#pragma unroll
+        for (int c = 0; c < 3; c++) { lo[c] = fmin(lo[c], bbk[q * 6 + c]); hi[c] = fmax(hi[c], bbk[q * 6 + 3 + c]); }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fmin(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmax(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+    const double inv = 1.0 / (2.0 * r_max * (1.0 + 1e-9));
+    double cells = 1.0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) cells *= floor((hi[c] - lo[c]) * inv) + 1.0;
+    return cells <= (double)EHIC_CELL_MAX;      // false for NaN extents
+}
 
 template <bool EXACT, int EHIC_PRIOR_THREADS>
 __global__ void __launch_bounds__(EHIC_PRIOR_THREADS)
 prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restrict__ beta,
              double *__restrict__ gprior, double *__restrict__ partP, int terms, double r_max,
-             const double *__restrict__ bbox)
+             const double *__restrict__ bbox, int cells_enabled)
 {
     const int k = blockIdx.y, r = blockIdx.z;
     const int b = blockIdx.x * EHIC_PRIOR_THREADS + threadIdx.x;
@@ -307,6 +333,16 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
     double g0 = 0.0, g1 = 0.0, g2 = 0.0;
     double e_nb = 0.0, e_bb = 0.0, e_sp = 0.0;
 
+    if ((terms & 2) && cells_enabled) {       // compact structure: cell_nonbonded_kernel takes the nonbonded term
+        __shared__ int s_fits;
+        if (threadIdx.x < 32) {
+            double lo[3], hi[3];
+            bool f = structure_fits_cells(bbox + ((long long)r * dm.S + k) * dm.n_slices * 6, dm.n_slices, r_max, threadIdx.x, lo, hi);
+            if (threadIdx.x == 0) s_fits = f ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_fits) terms &= ~2;
+    }
     if (terms & 2) {
         // partner tile: EHIC_PRIOR_TILE beads as (x, y), (z, radius), independent of the CTA size so
         // that small systems need one or two barriers per structure
@@ -485,6 +521,149 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
             for (int q = 0; q < EHIC_PRIOR_THREADS / 32; q++) { t0 += sh[0][q]; t1 += sh[1][q]; t2 += sh[2][q]; }
             double *o = partP + (((long long)r * dm.S + k) * gridDim.x + blockIdx.x) * 3;
             o[0] = t0; o[1] = t1; o[2] = t2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Cell-grid nonbonded kernel (fast mode): the GPU counterpart of the reference's production path,
+// a cubic cell grid of edge >= the largest contact range (c/nblist.c:112-303), rebuilt for every
+// evaluation like the reference does, but per structure inside ONE CTA:
+//   1. bounding box of the structure, grid dimensions (cell edge grows until the grid fits
+//      EHIC_CELL_MAX cells, as nblist.c:133-138 inflates its cells),
+//   2. counting sort of the beads by cell in shared memory; every cell's bead list is then sorted
+//      by bead index, so the layout -- and the summation order -- is deterministic,
+//   3. thread <-> bead: the 27 surrounding cells are scanned, contacts evaluated with the same
+//      arithmetic as prior_kernel (gather form: each pair seen from both ends, no atomics on FP data).
+// gprior += beta * dE_nb/dx (prior_kernel wrote the backbone / sphere part first);
+// partC[(r*S + k)] = sum a^4 over both visits.
+#define EHIC_CELL_THREADS 256
+
+__global__ void __launch_bounds__(EHIC_CELL_THREADS)
+cell_nonbonded_kernel(DevModel dm, const double *__restrict__ xs, const double *__restrict__ beta,
+                      double *__restrict__ gprior, double *__restrict__ partC, double r_max,
+                      int *__restrict__ scratch /* [R*S][N] sorted bead lists */, const double *__restrict__ bbox)
+{
+    __shared__ int s_start[EHIC_CELL_MAX + 1];
+    __shared__ int s_fill[EHIC_CELL_MAX];
+    __shared__ double s_red[6][EHIC_CELL_THREADS / 32];
+    __shared__ double s_box[7];
+    __shared__ int s_part[EHIC_CELL_THREADS];
+    __shared__ int s_G[3];
+    const int k = blockIdx.x, r = blockIdx.y;
+    const long long rk = (long long)r * dm.S + k;
+    const int N = dm.N, Np = dm.Np, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *xk = xs + rk * 3LL * Np;
+    int *list = scratch + rk * N;
+
+    // ---- 1. bounding box from the slice boxes; extended structures are left to prior_kernel --------
+    if (tid < 32) {
+        double lo[3], hi[3];
+        const bool fits = structure_fits_cells(bbox + rk * dm.n_slices * 6, dm.n_slices, r_max, tid, lo, hi);
+        if (tid == 0) {
+            const double edge = 2.0 * r_max * (1.0 + 1e-9), inv_e = 1.0 / edge;
+            for (int c = 0; c < 3; c++) {
+                s_box[c] = lo[c]; s_box[3 + c] = hi[c];
+                s_G[c] = fits ? (int)(floor((hi[c] - lo[c]) * inv_e) + 1.0) : 0;
+            }
+            s_box[6] = edge;
+        }
+    }
+    __syncthreads();
+    if (s_G[0] == 0) {
+        if (partC && tid == 0) partC[rk] = 0.0;
+        return;
+    }
+    const double edge = s_box[6], inv = 1.0 / edge;
+    const int G[3] = {s_G[0], s_G[1], s_G[2]};
+    const int ncell = G[0] * G[1] * G[2];
+    auto cell_of = [&](double x, double y, double z, int &ci, int &cj, int &ck) {
+        ci = min(max((int)floor((x - s_box[0]) * inv), 0), G[0] - 1);
+        cj = min(max((int)floor((y - s_box[1]) * inv), 0), G[1] - 1);
+        ck = min(max((int)floor((z - s_box[2]) * inv), 0), G[2] - 1);
+    };
+
+    // ---- 2. counting sort by cell ---------------------------------------------------------------
+    for (int q = tid; q < ncell; q += EHIC_CELL_THREADS) s_fill[q] = 0;
+    __syncthreads();
+    for (int b = tid; b < N; b += EHIC_CELL_THREADS) {
+        int ci, cj, ck; cell_of(xk[b], xk[Np + b], xk[2 * Np + b], ci, cj, ck);
+        atomicAdd(&s_fill[(ci * G[1] + cj) * G[2] + ck], 1);       // integer counts: order-independent
+    }
+    __syncthreads();
+    {   // exclusive scan of the counts (each thread a contiguous span, then the span totals)
+        const int span = (ncell + EHIC_CELL_THREADS - 1) / EHIC_CELL_THREADS;
+        const int q0 = min(tid * span, ncell), q1 = min(q0 + span, ncell);
+        int sum = 0;
+        for (int q = q0; q < q1; q++) sum += s_fill[q];
+        s_part[tid] = sum;
+        __syncthreads();
+        if (tid == 0) { int run = 0; for (int q = 0; q < EHIC_CELL_THREADS; q++) { int v = s_part[q]; s_part[q] = run; run += v; } s_start[ncell] = N; }
+        __syncthreads();
+        int run = s_part[tid];
+        for (int q = q0; q < q1; q++) { s_start[q] = run; run += s_fill[q]; }
+    }
+    __syncthreads();
+    for (int q = tid; q < ncell; q += EHIC_CELL_THREADS) s_fill[q] = 0;
+    __syncthreads();
+    for (int b = tid; b < N; b += EHIC_CELL_THREADS) {
+        int ci, cj, ck; cell_of(xk[b], xk[Np + b], xk[2 * Np + b], ci, cj, ck);
+        const int cell = (ci * G[1] + cj) * G[2] + ck;
+        list[s_start[cell] + atomicAdd(&s_fill[cell], 1)] = b;
+    }
+    __syncthreads();
+    for (int q = tid; q < ncell; q += EHIC_CELL_THREADS) {      // deterministic order inside every cell
+        const int a = s_start[q], e = s_start[q + 1];
+        for (int u = a + 1; u < e; u++) {
+            int v = list[u], w = u - 1;
+            while (w >= a && list[w] > v) { list[w + 1] = list[w]; w--; }
+            list[w + 1] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. contacts from the 27 surrounding cells ------------------------------------------------
+    const double bet = beta ? beta[r] : 1.0;
+    const double sc = bet * (dm.k_nb * 2.0);
+    double e_nb = 0.0;
+    for (int b = tid; b < N; b += EHIC_CELL_THREADS) {
+        const double xb0 = xk[b], xb1 = xk[Np + b], xb2 = xk[2 * Np + b];
+        const double rb = dm.radii[b];
+        int ci, cj, ck; cell_of(xb0, xb1, xb2, ci, cj, ck);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int di = max(ci - 1, 0); di <= min(ci + 1, G[0] - 1); di++)
+            for (int dj = max(cj - 1, 0); dj <= min(cj + 1, G[1] - 1); dj++) {
+                const int base = (di * G[1] + dj) * G[2];
+                const int u0 = s_start[base + max(ck - 1, 0)], u1 = s_start[base + min(ck + 1, G[2] - 1) + 1];
+                for (int u = u0; u < u1; u++) {          // the (up to) 3 cells along z are contiguous in the list
+                    const int o = list[u];
+                    if (o == b) continue;
+                    double dx = xk[o] - xb0, dy = xk[Np + o] - xb1, dz = xk[2 * Np + o] - xb2;
+                    double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    const double d0 = rb + dm.radii[o];
+                    if (s2 < d0 * d0) {
+                        double rd = rsqrt_nr(s2);
+                        double a = d0 - s2 * rd, aa = a * a;
+                        double g = aa * a * rd;
+                        a0 = fma(g, dx, a0); a1 = fma(g, dy, a1); a2 = fma(g, dz, a2);
+                        e_nb += aa * aa;
+                    }
+                }
+            }
+        if (gprior) {
+            double *o = gprior + (rk * N + b) * 3;
+            o[0] = fma(sc, a0, o[0]); o[1] = fma(sc, a1, o[1]); o[2] = fma(sc, a2, o[2]);
+        }
+    }
+    if (partC) {
+        e_nb = warp_sum(e_nb);
+        __syncthreads();
+        if (lane == 0) s_red[0][warp] = e_nb;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int q = 0; q < EHIC_CELL_THREADS / 32; q++) t += s_red[0][q];
+            partC[rk] = t;
         }
     }
 }
@@ -1129,6 +1308,7 @@ __global__ void __launch_bounds__(256)
 finalize_kernel(DevModel dm, const double *__restrict__ partA, int nA,
                 const double *__restrict__ partP, long long nP,
                 const double *__restrict__ partK, long long nK,
+                const double *__restrict__ partC, int nC,
                 double *__restrict__ energies, double *__restrict__ kinetic)
 {
     const int r = blockIdx.x;
@@ -1143,6 +1323,8 @@ finalize_kernel(DevModel dm, const double *__restrict__ partA, int nA,
         }
     if (partK)
         for (long long q = threadIdx.x; q < nK; q += 256) e3 += partK[(long long)r * nK + q];
+    if (partC)
+        for (int q = threadIdx.x; q < nC; q += 256) e0 += partC[(long long)r * nC + q];
     sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = e0; sh[2][threadIdx.x] = e1;
     sh[3][threadIdx.x] = e2; sh[4][threadIdx.x] = e3;
     __syncthreads();

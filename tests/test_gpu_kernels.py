@@ -309,3 +309,45 @@ def test_one_launch_trajectory_equals_multi_kernel_trajectory(monkeypatch, S, N,
     assert relerr(res["small"][0], res["multi"][0]) < 1e-12
     assert relerr(res["small"][1], res["multi"][1]) < 1e-10
     np.testing.assert_allclose(res["small"][2], res["multi"][2], rtol=1e-11)
+
+
+# ---- cell-grid nonbonded path ------------------------------------------------------------------------
+
+def _ball(rng, n, radius):
+    v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    return v * (radius * rng.random(n) ** (1 / 3.0))[:, None]
+
+
+@pytest.mark.parametrize("N,force", [(4100, False), (1100, True), (150, True), (64, True), (333, True)])
+def test_cell_grid_nonbonded_matches_oracle(co, monkeypatch, N, force):
+    """compact structures take the cell grid, extended ones the pruned all-pairs sweep -- in the same call"""
+    from ensemble_hic_b200.engine import TERM_NONBONDED, TERM_ALL
+    if force:
+        monkeypatch.setenv("EHIC_NB", "cells")
+    rng = np.random.default_rng(N)
+    radii = rng.uniform(0.4, 0.6, N)
+    compact = _ball(rng, N, 0.62 * N ** (1 / 3.0))                       # ~1 bead per unit volume: many contacts
+    extended = make_problem(seed=N, S=1, N=N, step=0.9)["X"][0]           # random walk: grid would not fit -> all-pairs
+    walk = make_problem(seed=N + 1, S=1, N=N, step=0.45)["X"][0]
+    degenerate = np.zeros((N, 3)); degenerate[:, 0] = np.arange(N) * 0.8  # a straight line: 1 x 1 x many cells
+    X = np.stack([compact, extended, walk, degenerate])
+    from ensemble_hic_b200.engine import Model
+    m = Model(4, radii, k_nb=50.0, k_bb=0.0, max_replicas=2)
+    Xr = np.stack([X, X[::-1]])
+    out = m.evaluate(Xr, None, None, np.array([1.0, 0.3]), terms=TERM_NONBONDED, energies=True)
+    ref_g = np.concatenate([co.forcefield_gradient(x, radii, radii * radii, 50.0) for x in X]).reshape(4, -1)
+    ref_E = np.array([co.forcefield_energy(x, radii, radii * radii, 50.0) for x in X])
+    assert (np.abs(ref_g).max(axis=1) > 0).all()
+    assert relerr(out["grad"][0].reshape(4, -1), ref_g) < FAST_TOL
+    assert relerr(out["grad"][1].reshape(4, -1), 0.3 * ref_g[::-1]) < FAST_TOL
+    assert abs(out["energies"][0, 1] - ref_E.sum()) <= 1e-12 * ref_E.sum()
+    assert abs(out["energies"][1, 1] - ref_E.sum()) <= 1e-12 * ref_E.sum()
+    # the two nonbonded paths agree with each other, with backbone fused in
+    monkeypatch.setenv("EHIC_NB", "pairs")
+    m2 = Model(4, radii, k_nb=50.0, k_bb=500.0, max_replicas=2)
+    monkeypatch.setenv("EHIC_NB", "cells")
+    m3 = Model(4, radii, k_nb=50.0, k_bb=500.0, max_replicas=2)
+    a = m2.evaluate(Xr, None, None, np.array([1.0, 0.3]), terms=TERM_ALL, energies=True)
+    b = m3.evaluate(Xr, None, None, np.array([1.0, 0.3]), terms=TERM_ALL, energies=True)
+    assert relerr(a["grad"], b["grad"]) < 1e-13
+    np.testing.assert_allclose(a["energies"], b["energies"], rtol=1e-12)

@@ -12,7 +12,20 @@ def main():
     i, j = np.triu_indices(N, 2)
     M = len(i)
     radii = np.full(N, 0.5)
-    X = np.stack([random_walk(rng, S, N, 0.9) for _ in range(R)])
+    if os.environ.get("QB_COMPACT"):
+        # compact globules: reflecting random walk inside a ball holding ~1 bead per unit volume
+        rad = 0.62 * N ** (1 / 3.0)
+        X = np.zeros((R, S, N, 3))
+        for r_ in range(R):
+            for k in range(S):
+                p = np.zeros(3)
+                steps = rng.normal(size=(N, 3)); steps *= 0.9 / np.linalg.norm(steps, axis=1, keepdims=True)
+                for bi in range(N):
+                    q = p + steps[bi]
+                    if np.linalg.norm(q) > rad: q = p - steps[bi]
+                    X[r_, k, bi] = p = q
+    else:
+        X = np.stack([random_walk(rng, S, N, 0.9) for _ in range(R)])
     cds = np.full(M, 1.25)
     d = np.linalg.norm(X[0][:, i] - X[0][:, j], axis=2) if N <= 500 else None
     counts = rng.poisson(2.0, size=M)
