@@ -82,7 +82,8 @@ struct ehic_model {
     std::vector<Timed> timed;
     // staging for the host entry points
     double *st_x = nullptr, *st_g = nullptr, *st_md = nullptr, *st_small = nullptr;
-    cudaStream_t st_stream = nullptr;
+    cudaStream_t st_stream = nullptr, st_in = nullptr, st_out = nullptr;
+    cudaEvent_t ev_in[4] = {nullptr, nullptr, nullptr, nullptr}, ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 static void drop_graphs(ehic_model *m)
@@ -354,9 +355,13 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     if (cudaMemset(m->wbuf, 0, Rm * (size_t)dm.wstride * sizeof(double)) != cudaSuccess) {
         ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed");
     }
-    if (cudaStreamCreateWithFlags(&m->st_stream, cudaStreamNonBlocking) != cudaSuccess) {
-        ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaStreamCreate failed");
-    }
+    bool ok = cudaStreamCreateWithFlags(&m->st_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&m->st_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&m->st_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int q = 0; ok && q < 4; q++)
+        ok = cudaEventCreateWithFlags(&m->ev_in[q], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&m->ev_done[q], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "stream / event creation failed"); }
     *out = m;
     return EHIC_OK;
 }
@@ -369,6 +374,9 @@ int ehic_model_destroy(ehic_model_t *m)
     for (void *p : m->owned) cudaFree(p);
     cudaFree(m->st_x); cudaFree(m->st_g); cudaFree(m->st_md); cudaFree(m->st_small);
     if (m->st_stream) cudaStreamDestroy(m->st_stream);
+    if (m->st_in) cudaStreamDestroy(m->st_in);
+    if (m->st_out) cudaStreamDestroy(m->st_out);
+    for (int q = 0; q < 4; q++) { if (m->ev_in[q]) cudaEventDestroy(m->ev_in[q]); if (m->ev_done[q]) cudaEventDestroy(m->ev_done[q]); }
     delete m;
     return EHIC_OK;
 }
@@ -849,21 +857,39 @@ int ehic_evaluate_host(ehic_model_t *m, int R, int terms, const double *h_x, con
     if (!h_x) return fail(EHIC_ERR_INVALID, "null coordinates");
     rc = ensure_staging(m);
     if (rc) return rc;
-    cudaStream_t st = m->st_stream;
-    const size_t nx = (size_t)R * m->dm.S * (size_t)m->dm.N * 3;
+    // Software pipeline over chunks of replicas on three streams: the H2D copy of chunk c+1 and the
+    // D2H copy of chunk c-1 overlap the kernels of chunk c (kernels run one chunk at a time, so the
+    // model's workspace is reused).  Over PCIe the two 38 MB copies of config D would otherwise add
+    // ~20 % to the step.
+    cudaStream_t st = m->st_stream, s_in = m->st_in, s_out = m->st_out;
+    const size_t per = (size_t)m->dm.S * (size_t)m->dm.N * 3;
+    const size_t M = (size_t)m->dm.M;
     double *d_norm = m->st_small, *d_lam = m->st_small + m->max_replicas, *d_bet = m->st_small + 2 * (size_t)m->max_replicas;
     double *d_E = m->st_small + 3 * (size_t)m->max_replicas;   // 4 * Rmax
-    CU(cudaMemcpyAsync(m->st_x, h_x, sizeof(double) * nx, cudaMemcpyHostToDevice, st));
-    if (h_norm) CU(cudaMemcpyAsync(d_norm, h_norm, sizeof(double) * R, cudaMemcpyHostToDevice, st));
-    if (h_lammda) CU(cudaMemcpyAsync(d_lam, h_lammda, sizeof(double) * R, cudaMemcpyHostToDevice, st));
-    if (h_beta) CU(cudaMemcpyAsync(d_bet, h_beta, sizeof(double) * R, cudaMemcpyHostToDevice, st));
-    rc = ehic_evaluate(m, R, terms, m->st_x, h_norm ? d_norm : nullptr, h_lammda ? d_lam : nullptr,
-                       h_beta ? d_bet : nullptr, h_grad ? m->st_g : nullptr, h_energies ? d_E : nullptr,
-                       h_md ? m->st_md : nullptr, st);
-    if (rc) return rc;
-    if (h_grad) CU(cudaMemcpyAsync(h_grad, m->st_g, sizeof(double) * nx, cudaMemcpyDeviceToHost, st));
-    if (h_energies) CU(cudaMemcpyAsync(h_energies, d_E, sizeof(double) * 4 * R, cudaMemcpyDeviceToHost, st));
-    if (h_md && m->dm.M > 0) CU(cudaMemcpyAsync(h_md, m->st_md, sizeof(double) * (size_t)R * m->dm.M, cudaMemcpyDeviceToHost, st));
+    if (h_norm) CU(cudaMemcpyAsync(d_norm, h_norm, sizeof(double) * R, cudaMemcpyHostToDevice, s_in));
+    if (h_lammda) CU(cudaMemcpyAsync(d_lam, h_lammda, sizeof(double) * R, cudaMemcpyHostToDevice, s_in));
+    if (h_beta) CU(cudaMemcpyAsync(d_bet, h_beta, sizeof(double) * R, cudaMemcpyHostToDevice, s_in));
+    const int n_chunks = std::min(R, 4);
+    for (int c = 0; c < n_chunks; c++) {
+        const int r0 = (int)((long long)R * c / n_chunks), r1 = (int)((long long)R * (c + 1) / n_chunks);
+        CU(cudaMemcpyAsync(m->st_x + r0 * per, h_x + r0 * per, sizeof(double) * per * (r1 - r0), cudaMemcpyHostToDevice, s_in));
+        CU(cudaEventRecord(m->ev_in[c], s_in));
+    }
+    for (int c = 0; c < n_chunks; c++) {
+        const int r0 = (int)((long long)R * c / n_chunks), r1 = (int)((long long)R * (c + 1) / n_chunks);
+        CU(cudaStreamWaitEvent(st, m->ev_in[c], 0));
+        rc = ehic_evaluate(m, r1 - r0, terms, m->st_x + r0 * per, h_norm ? d_norm + r0 : nullptr,
+                           h_lammda ? d_lam + r0 : nullptr, h_beta ? d_bet + r0 : nullptr,
+                           h_grad ? m->st_g + r0 * per : nullptr, h_energies ? d_E + 4 * (size_t)r0 : nullptr,
+                           h_md ? m->st_md + r0 * M : nullptr, st);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        CU(cudaEventRecord(m->ev_done[c], st));
+        CU(cudaStreamWaitEvent(s_out, m->ev_done[c], 0));
+        if (h_grad) CU(cudaMemcpyAsync(h_grad + r0 * per, m->st_g + r0 * per, sizeof(double) * per * (r1 - r0), cudaMemcpyDeviceToHost, s_out));
+        if (h_md && M > 0) CU(cudaMemcpyAsync(h_md + r0 * M, m->st_md + r0 * M, sizeof(double) * M * (r1 - r0), cudaMemcpyDeviceToHost, s_out));
+    }
+    if (h_energies) CU(cudaMemcpyAsync(h_energies, d_E, sizeof(double) * 4 * R, cudaMemcpyDeviceToHost, s_out));
+    CU(cudaStreamSynchronize(s_out));
     CU(cudaStreamSynchronize(st));
     return EHIC_OK;
 }
