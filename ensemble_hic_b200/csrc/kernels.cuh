@@ -1036,6 +1036,25 @@ __device__ __forceinline__ void reduce8(double (&r)[8], int lane)
     r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
 }
 
+// Same for 4 values: after the call r[0] of lane L is the total of column ((L>>3)&1) + 2*((L>>4)&1).
+__device__ __forceinline__ void reduce4(double (&r)[4], int lane)
+{
+    bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        double send = hi ? r[i] : r[i + 2], keep = hi ? r[i + 2] : r[i];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    hi = (lane & 8) != 0;
+    {
+        double send = hi ? r[0] : r[1], keep = hi ? r[1] : r[0];
+        r[0] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    r[0] += __shfl_xor_sync(0xffffffffu, r[0], 4);
+    r[0] += __shfl_xor_sync(0xffffffffu, r[0], 2);
+    r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+}
+
 // Backward, tile form: CTA <-> (replica, row block of 128 beads, group of 4 structures); warp <->
 // structure; each lane owns 4 row beads (accumulated in registers over all column slices of the row
 // block).  The (contact distance, weight) slots do not depend on the structure: chunks of 8 columns
@@ -1061,19 +1080,25 @@ struct BackwardTileArgs {
     double r_max;
 };
 
+#ifndef EHIC_BT_NC
+#define EHIC_BT_NC 8        // columns whose reactions are reduced together (8 or 4)
+#endif
+
 template <bool MASKED, bool NB>
-__device__ __forceinline__ void backward_chunk(const DevModel &dm, const double *__restrict__ sd, int qg, int lane,
+__device__ __forceinline__ void backward_chunk(const DevModel &dm, const double *__restrict__ sd, int qbase, int lane,
                                                double cx, double cy, double cz, double cr, const unsigned (&m)[4],
                                                int row0, int col0, const double (&xb)[4][3],
                                                double coarse, double nbs,
-                                               double (&acc)[4][3], double (&rx)[8], double (&ry)[8], double (&rz)[8])
+                                               double (&acc)[4][3], double (&rx)[EHIC_BT_NC], double (&ry)[EHIC_BT_NC],
+                                               double (&rz)[EHIC_BT_NC])
 {
+    // qbase = first column of this group inside the tile; sd points at the group's slots;
     // row0 = first bead of this lane's rows (row rb is row0 + 32 rb); coarse = (2 r_max)^2
     const double alpha = dm.alpha;
     unsigned hits = 0u;                       // bit (qq * 4 + rb): pair within the coarse contact range
 #pragma unroll
-    for (int qq = 0; qq < 8; qq++) {
-        const int q = qg * 8 + qq;
+    for (int qq = 0; qq < EHIC_BT_NC; qq++) {
+        const int q = qbase + qq;
         const double ox = __shfl_sync(0xffffffffu, cx, q), oy = __shfl_sync(0xffffffffu, cy, q),
                      oz = __shfl_sync(0xffffffffu, cz, q);
         double fx = 0.0, fy = 0.0, fz = 0.0;
@@ -1103,9 +1128,9 @@ __device__ __forceinline__ void backward_chunk(const DevModel &dm, const double 
         const unsigned any = __reduce_or_sync(0xffffffffu, hits);
         if (any != 0u) {
 #pragma unroll
-            for (int qq = 0; qq < 8; qq++) {
+            for (int qq = 0; qq < EHIC_BT_NC; qq++) {
                 if (((any >> (qq * 4)) & 15u) == 0u) continue;
-                const int q = qg * 8 + qq;
+                const int q = qbase + qq;
                 const double ox = __shfl_sync(0xffffffffu, cx, q), oy = __shfl_sync(0xffffffffu, cy, q),
                              oz = __shfl_sync(0xffffffffu, cz, q), ro = __shfl_sync(0xffffffffu, cr, q);
 #pragma unroll
@@ -1218,19 +1243,31 @@ backward_tile_kernel(DevModel dm, TileDev td, BackwardTileArgs ba)
                 for (int rb = 0; rb < 4; rb++) m[rb] = td.mask[((long long)t * 4 + rb) * 32 + lane];
             }
         }
-        const double *sd = smem + (c % EHIC_BT_STAGES) * 2048 + lane;
-        double rx[8], ry[8], rz[8];
-        if (NB && nb_tile) {
-            if (clean) backward_chunk<false, true>(dm, sd, qg, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
-            else backward_chunk<true, true>(dm, sd, qg, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
-        } else {
-            if (clean) backward_chunk<false, false>(dm, sd, qg, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
-            else backward_chunk<true, false>(dm, sd, qg, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
-        }
-        reduce8(rx, lane); reduce8(ry, lane); reduce8(rz, lane);
-        if ((lane & 3) == 0 && k_ok) {
-            const int col = col0 + qg * 8 + (((lane >> 2) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 4) & 1));
-            if (col < dm.N) { double *o = Pk + (long long)col * 3; o[0] = rx[0]; o[1] = ry[0]; o[2] = rz[0]; }
+#pragma unroll
+        for (int h = 0; h < 8 / EHIC_BT_NC; h++) {
+            const int qbase = qg * 8 + h * EHIC_BT_NC;
+            const double *sd = smem + (c % EHIC_BT_STAGES) * 2048 + h * EHIC_BT_NC * 128 + lane;
+            double rx[EHIC_BT_NC], ry[EHIC_BT_NC], rz[EHIC_BT_NC];
+            if (NB && nb_tile) {
+                if (clean) backward_chunk<false, true>(dm, sd, qbase, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
+                else backward_chunk<true, true>(dm, sd, qbase, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
+            } else {
+                if (clean) backward_chunk<false, false>(dm, sd, qbase, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
+                else backward_chunk<true, false>(dm, sd, qbase, lane, cx, cy, cz, cr, m, row0, col0, xb, coarse, nbs, acc, rx, ry, rz);
+            }
+#if EHIC_BT_NC == 8
+            reduce8(rx, lane); reduce8(ry, lane); reduce8(rz, lane);
+            const bool writer = (lane & 3) == 0;
+            const int sub = ((lane >> 2) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 4) & 1);
+#else
+            reduce4(rx, lane); reduce4(ry, lane); reduce4(rz, lane);
+            const bool writer = (lane & 7) == 0;
+            const int sub = ((lane >> 3) & 1) + 2 * ((lane >> 4) & 1);
+#endif
+            if (writer && k_ok) {
+                const int col = col0 + qbase + sub;
+                if (col < dm.N) { double *o = Pk + (long long)col * 3; o[0] = rx[0]; o[1] = ry[0]; o[2] = rz[0]; }
+            }
         }
     }
     if (k_ok) {
