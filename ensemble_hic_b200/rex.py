@@ -82,7 +82,9 @@ class EngineBackend(object):
 
     def trajectory(self, x, p, norm, lam, beta, eps, n_steps):
         R = x.shape[0]
-        H = self.torch.empty(R, 4, dtype=self.torch.float64, device=self.device)
+        if getattr(self, "_H", None) is None or self._H.shape[0] != R:      # persistent: part of the graph signature
+            self._H = self.torch.empty(R, 4, dtype=self.torch.float64, device=self.device)
+        H = self._H
         with self.torch.cuda.device(self.device):
             self.m.hmc_trajectory_device(R, n_steps, x, p, norm, lam, beta, eps, H)
         return H
@@ -173,12 +175,19 @@ class ReplicaExchange(object):
         be, temps = self.be, self._local_temps()
         lam, bet = be.tensor(self.lam_T[temps]), be.tensor(self.bet_T[temps])
         eps = be.tensor(self.timestep_T[temps])
+        # persistent work buffers: the device pointers are part of the trajectory graph's signature
+        if getattr(self, "_x_work", None) is None:
+            self._x_work = be.torch.empty_like(self.x)
+            self._p_work = be.torch.empty_like(self.x)
+            self._lam_w, self._bet_w, self._eps_w = lam.clone(), bet.clone(), eps.clone()
         if self.momenta == "numpy":
-            p = be.tensor(np.stack([rs.normal(size=be.n_dof) for rs in self.rng_slot]))
+            self._p_work.copy_(be.tensor(np.stack([rs.normal(size=be.n_dof) for rs in self.rng_slot])))
         else:
-            p = be.torch.randn(self.R, be.n_dof, dtype=be.torch.float64, device=self.x.device)
-        x_new = self.x.clone()
-        H = be.trajectory(x_new, p, self.norm, lam, bet, eps, self.L)
+            self._p_work.normal_()
+        x_new, p = self._x_work, self._p_work
+        x_new.copy_(self.x)
+        self._lam_w.copy_(lam); self._bet_w.copy_(bet); self._eps_w.copy_(eps)
+        H = be.trajectory(x_new, p, self.norm, self._lam_w, self._bet_w, self._eps_w, self.L)
         Hh = H.detach().cpu().numpy()
         dH = (Hh[:, 2] + Hh[:, 3]) - (Hh[:, 0] + Hh[:, 1])
         u = np.array([rs.random_sample() for rs in self.rng_slot])
@@ -205,7 +214,7 @@ class ReplicaExchange(object):
                 rate = lam_q * sums[q] + self.norm_prior[1]
                 v = self.rng_slot[q].gamma(shape) / rate
                 new[q] = v if v != 0.0 else 1e-10
-            self.norm = be.tensor(new)
+            self.norm.copy_(be.tensor(new))
         return acc
 
     # ---- one exchange round ----------------------------------------------------------------------------
