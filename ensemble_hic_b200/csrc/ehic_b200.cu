@@ -470,10 +470,19 @@ static int launch_forward(ehic_model *m, int R, const double *xs, const double *
         return EHIC_OK;
     }
     dim3 grid((unsigned)m->nA, (unsigned)R);
+    static const bool fwd_soa = []() { const char *e = getenv("EHIC_FORWARD"); return e && !strcmp(e, "soa"); }();
     if (m->flags & EHIC_FLAG_EXACT)
         forward_kernel<true><<<grid, 256, 0, st>>>(m->dm, xs, d_norm, d_md, want_w ? m->wbuf : nullptr, m->partA, want_logl);
-    else
+    else if (fwd_soa)
         forward_kernel<false><<<grid, 256, 0, st>>>(m->dm, xs, d_norm, d_md, want_w ? m->wbuf : nullptr, m->partA, want_logl);
+    else {
+        double *wb = want_w ? m->wbuf : nullptr;
+        switch (m->kt) {
+        case 4: forward_rec_kernel<4><<<grid, 256, 0, st>>>(m->dm, m->xt[m->cur_xt], d_norm, d_md, wb, m->partA, want_logl, m->nkt); break;
+        case 2: forward_rec_kernel<2><<<grid, 256, 0, st>>>(m->dm, m->xt[m->cur_xt], d_norm, d_md, wb, m->partA, want_logl, m->nkt); break;
+        default: forward_rec_kernel<1><<<grid, 256, 0, st>>>(m->dm, m->xt[m->cur_xt], d_norm, d_md, wb, m->partA, want_logl, m->nkt); break;
+        }
+    }
     LAUNCHED();
     CU(cudaGetLastError());
     return EHIC_OK;
@@ -590,7 +599,7 @@ int ehic_mock_data(ehic_model_t *m, int R, const double *d_x, const double *d_no
     if (rc) return rc;
     if (!d_x || !d_norm || !d_md) return fail(EHIC_ERR_INVALID, "null buffer");
     cudaStream_t st = (cudaStream_t)stream;
-    rc = launch_pack(m, R, d_x, m->xs[0], m->use_tiles ? m->xt[0] : nullptr, st);
+    rc = launch_pack(m, R, d_x, m->xs[0], (m->flags & EHIC_FLAG_EXACT) ? nullptr : m->xt[0], st);
     if (rc) return rc;
     m->cur_xt = 0;
     return launch_forward(m, R, m->xs[0], d_norm, d_md, false, false, st);
@@ -610,7 +619,7 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     const int prior_terms = terms & ~EHIC_TERM_LIKELIHOOD;
     if ((lik || d_md) && !d_norm) return fail(EHIC_ERR_INVALID, "norm required for the likelihood term");
     cudaStream_t st = (cudaStream_t)stream;
-    rc = launch_pack(m, R, d_x, m->xs[0], (d_grad || m->use_tiles) ? m->xt[0] : nullptr, st);
+    rc = launch_pack(m, R, d_x, m->xs[0], (d_grad || !(m->flags & EHIC_FLAG_EXACT)) ? m->xt[0] : nullptr, st);
     if (rc) return rc;
     m->cur_xt = 0;
     const bool need_forward = (lik && (d_grad || d_energies)) || d_md;

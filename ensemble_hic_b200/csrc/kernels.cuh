@@ -246,6 +246,90 @@ __device__ __forceinline__ void load_record(const double *__restrict__ p, double
 }
 
 // ---------------------------------------------------------------------------------------
+// Forward kernel of the row path, fast mode: same mapping as forward_kernel (thread <-> pair of the
+// (i, j)-sorted list, serial over the ensemble), but both beads are read as tile-AoS records:
+// 12 LDG.128 per KT structures instead of 6 LDG.64 per structure.  On sparse lists, where every
+// partner is its own cache line, that is KT times fewer sectors from L2 (the SoA version is bound
+// by L2 sector traffic there, profiles/r01_sparse_rowpath_E.txt).
+template <int KT>
+__global__ void __launch_bounds__(256)
+forward_rec_kernel(DevModel dm, const double *__restrict__ xt, const double *__restrict__ norm,
+                   double *__restrict__ md_out, double *__restrict__ wbuf,
+                   double *__restrict__ partA, int want_logl, int nkt)
+{
+    const int r = blockIdx.y;
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const double nrm = norm[r];
+    double term = 0.0;
+    if (m < dm.M) {
+        const int i = dm.pi[m], j = dm.pj[m];
+        const double dc = dm.pdc[m], c = dm.pcnt[m];
+        const double alpha = dm.alpha;
+        const double *ra = xt + ((long long)r * nkt * dm.Np + i) * (KT * 3);
+        const double *rb = xt + ((long long)r * nkt * dm.Np + j) * (KT * 3);
+        const long long step = (long long)dm.Np * (KT * 3);
+        double acc[KT];
+#pragma unroll
+        for (int t = 0; t < KT; t++) acc[t] = 0.0;
+        const int nfull = dm.S / KT;
+        for (int kt = 0; kt < nfull; kt++, ra += step, rb += step) {
+            double a[KT * 3], b[KT * 3];
+            load_record<KT>(ra, a); load_record<KT>(rb, b);
+#pragma unroll
+            for (int t = 0; t < KT; t++) {
+                double dx = a[3 * t] - b[3 * t], dy = a[3 * t + 1] - b[3 * t + 1], dz = a[3 * t + 2] - b[3 * t + 2];
+                double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                double rd = rsqrt_nr(s2);
+                double tt = alpha * (dc - s2 * rd);
+                double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                acc[t] += fma(tt, rq, 1.0);
+            }
+        }
+        if (nfull < nkt) {
+            double a[KT * 3], b[KT * 3];
+            load_record<KT>(ra, a); load_record<KT>(rb, b);
+            const int nvalid = dm.S - nfull * KT;
+#pragma unroll
+            for (int t = 0; t < KT; t++) {
+                if (t < nvalid) {
+                    double dx = a[3 * t] - b[3 * t], dy = a[3 * t + 1] - b[3 * t + 1], dz = a[3 * t + 2] - b[3 * t + 2];
+                    double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    double rd = rsqrt_nr(s2);
+                    double tt = alpha * (dc - s2 * rd);
+                    double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                    acc[t] += fma(tt, rq, 1.0);
+                }
+            }
+        }
+        double sum = 0.0;
+#pragma unroll
+        for (int t = 0; t < KT; t++) sum += acc[t];
+        const double md = sum * (0.5 * nrm);
+        if (md_out) md_out[(long long)r * dm.M + dm.perm[m]] = md;
+        double em = __dsub_rn(1.0, __ddiv_rn(c, md));
+        double w = __dmul_rn(__dmul_rn(__dmul_rn(0.5, em), nrm), alpha);
+        if (wbuf) {
+            double *wr = wbuf + (long long)r * dm.wstride;
+            wr[dm.slot_a[m]] = w;
+            wr[dm.slot_b[m]] = w;
+        }
+        if (want_logl) term = c * log(md) - md;
+    }
+    if (want_logl) {
+        __shared__ double sh[8];
+        double v = warp_sum(term);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) t += sh[q];
+            partA[(long long)r * gridDim.x + blockIdx.x] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Bounding boxes of the 32-bead slices of every structure: bbox[R*S][n_slices][6] = (lo, hi).
 // Consecutive beads of a chain are neighbours in space, so the all-pairs sweep of the prior kernel
 // can discard whole 32 x 32 slice pairs whose boxes are farther apart than the largest contact
