@@ -1,17 +1,28 @@
-"""Conjugate Gibbs sampler for the scaling factor (reference: npsamplers.py:42-116).
+"""Gibbs update of the scaling factor ``norm`` (reference counterpart: npsamplers.py).
 
-With a Poisson error model and a Gamma(shape a, rate b) prior, norm | structures is
-Gamma(lammda * sum(c) + a, lammda * sum(fwm(norm=1)) + b).  The only expensive piece, the
-forward-model evaluation at norm = 1, runs on the GPU."""
+Poisson counts with rates norm * f_m and a Gamma(a, b) prior on norm are conjugate:
+
+    norm | structures, data  ~  Gamma( lammda * sum_m c_m + a ,  lammda * sum_m f_m + b ),
+
+where f = forward model evaluated at norm = 1 and lammda is the likelihood temperature.  The one
+expensive ingredient, f, is a forward-kernel launch on the GPU (``L.forward_model(norm=1.0)``);
+everything else is scalar host arithmetic with numpy's global RNG, as in the reference.
+"""
 import numpy as np
 
 
 class AbstractGammaSampler(object):
+    """Draws ``state ~ Gamma(shape, rate)``; subclasses say what shape and rate are.
+
+    ``pdf`` is assigned by the Gibbs sampler before every draw: the posterior conditioned on all
+    other variables."""
+
     pdf = None
 
     def __init__(self, likelihood_name, variable_name):
         self._likelihood_name = likelihood_name
         self._variable_name = variable_name
+        self.state = None
 
     def _calculate_shape(self):
         raise NotImplementedError
@@ -19,22 +30,32 @@ class AbstractGammaSampler(object):
     def _calculate_rate(self):
         raise NotImplementedError
 
-    def sample(self, state=42):
+    def conditional_parameters(self):
+        """(shape, rate) of the conditional Gamma, rate first evaluated like the reference does"""
         rate = self._calculate_rate()
-        shape = self._calculate_shape()
-        sample = np.random.gamma(shape) / rate
-        if sample == 0.0:
-            sample += 1e-10
-        self.state = sample
+        return self._calculate_shape(), rate
+
+    def sample(self, state=42):
+        shape, rate = self.conditional_parameters()
+        draw = np.random.gamma(shape) / rate
+        self.state = draw if draw != 0.0 else 1e-10      # a zero scale would make log(md) diverge
         return self.state
 
 
 class NormGammaSampler(AbstractGammaSampler):
+    """sampler for 'norm' under the 'ensemble_contacts' likelihood with a Poisson error model"""
+
     def __init__(self):
         super(NormGammaSampler, self).__init__("ensemble_contacts", "norm")
 
+    def _likelihood(self):
+        return self.pdf.likelihoods[self._likelihood_name]
+
     def _get_prior(self):
-        return [p for p in self.pdf.priors.values() if "norm" in p._original_variables][0]
+        for prior in self.pdf.priors.values():
+            if "norm" in prior._original_variables:
+                return prior
+        raise KeyError("the posterior has no prior on 'norm'")
 
     def _check_gamma_prior(self, prior):
         from .gamma_prior import GammaPrior
@@ -43,12 +64,11 @@ class NormGammaSampler(AbstractGammaSampler):
     def _calculate_shape(self):
         prior = self._get_prior()
         if not self._check_gamma_prior(prior):
-            raise NotImplementedError("only Gamma priors are supported for the scaling parameter")
-        L = self.pdf.likelihoods[self._likelihood_name]
-        return L["lammda"].value * np.sum(L.error_model.data) + prior["shape"].value
+            raise NotImplementedError("the scaling factor can only be sampled under a Gamma prior")
+        L = self._likelihood()
+        return L["lammda"].value * float(np.sum(L.error_model.data)) + prior["shape"].value
 
     def _calculate_rate(self):
-        prior = self._get_prior()
-        L = self.pdf.likelihoods[self._likelihood_name]
-        md = L.forward_model(norm=1.0)
-        return L["lammda"].value * md.sum() + prior["rate"].value
+        L = self._likelihood()
+        unscaled = L.forward_model(norm=1.0)             # GPU forward kernel
+        return L["lammda"].value * float(unscaled.sum()) + self._get_prior()["rate"].value
