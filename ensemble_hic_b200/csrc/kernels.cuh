@@ -43,15 +43,23 @@ struct DevModel {
 // Full-precision 1/sqrt(x) for normal x > 0: MUFU.RSQ64H seed (~2^-22) + one third-order
 // step (error ~ (5/16) e^3 < 2^-60).  5 FP64 instructions, no slow path; x = 0 gives inf/NaN
 // exactly where the reference divides by zero.
+#ifndef EHIC_RSQRT_ORDER
+#define EHIC_RSQRT_ORDER 3
+#endif
 __device__ __forceinline__ double rsqrt_nr(double x)
 {
     double y0;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
     double a = x * y0;
     double e = fma(-a, y0, 1.0);
+#if EHIC_RSQRT_ORDER == 3
     double p = fma(0.375, e, 0.5);
     double ye = y0 * e;
     return fma(ye, p, y0);
+#else   // second order: 4 FP64 instructions, relative error ~1.5 * seed_error^2 (~1e-13)
+    double h = 0.5 * y0;
+    return fma(h, e, y0);
+#endif
 }
 
 __device__ __forceinline__ double warp_sum(double v)
