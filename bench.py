@@ -348,7 +348,7 @@ def run_b200(args):
         if os.path.exists(pj):
             with open(pj) as f:
                 prof = json.load(f)
-        tiles = model.info()["kt"] >= 10000
+        tiles = model.info()["path"] == "tiles"
         roofline = {"bound": "fp64", "kernel": "backward_tile_kernel" if tiles else "gather_kernel", "achieved": ach, "peak": fp64_tf, "unit": "TFLOP/s",
                     "frac": (ach / fp64_tf) if ach else None, "traffic": prof.get("gather_dram_bytes_per_launch"),
                     "peak_source": "measured here: DFMA issue-rate micro-benchmark (ehic_fma_peak); FP64/FP32 "

@@ -53,6 +53,9 @@ struct ehic_model {
     bool nb_fused = false;          // tiles cover all bead pairs: nonbonded force rides in the backward tile kernel
     const unsigned char *tile_clean = nullptr;
     TileDev td{};
+    bool use_lanes = false;         // sparse list + fast mode + enough structures to fill warps: lane path
+    LaneDev ld{};
+    int n_quads = 0;                // lane path: backward CTAs per (replica, structure group)
     double tile_fill = 0.0;
     int nA_tile = 0, nKc = 0;       // forward-tile blocks per replica; combine blocks per structure
     double *tw = nullptr, *Grow = nullptr, *Pbuf = nullptr;
@@ -247,7 +250,7 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         const char *path = getenv("EHIC_PATH");
         const char *mf = getenv("EHIC_TILE_MIN_FILL");
         double min_fill = mf ? atof(mf) : 0.5;
-        bool want = !exact && !(path && !strcmp(path, "rows"));
+        bool want = !exact && !(path && (!strcmp(path, "rows") || !strcmp(path, "lanes")));
         if (path && !strcmp(path, "tiles")) min_fill = 0.0;
         if (want && desc->n_data > 0) build_tiles(L, desc->data_points, desc->contact_distances, min_fill, TL);
         m->use_tiles = TL.eligible;
@@ -277,12 +280,39 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         // pruning the separate prior kernel is cheaper than the extra registers the fused variant needs
         { const char *nf = getenv("EHIC_NB_FUSED"); m->nb_fused = TL.covers_all_pairs && nf && !strcmp(nf, "1"); }
     }
+    // sparse lists in fast mode take the lane path (lane <-> structure) when the ensemble fills at least
+    // 60 % of the lanes of its structure groups; EHIC_PATH=lanes|rows overrides
+    if (!exact && !m->use_tiles && desc->n_data > 0) {
+        const char *path = getenv("EHIC_PATH");
+        const int nkg = (S + 31) / 32;
+        bool want = (double)S >= 0.6 * 32.0 * nkg;
+        if (path && !strcmp(path, "lanes")) want = true;
+        if (path && !strcmp(path, "rows")) want = false;
+        if (want) {
+            LaneLayout LL;
+            err = build_lanes(L, LL);
+            if (!err.empty()) { ehic_model_destroy(m); return fail(EHIC_ERR_INVALID, err); }
+            std::vector<LanePair> pairs((size_t)L.M);
+            for (int64_t s = 0; s < L.M; s++) { pairs[s].i = L.pi[s]; pairs[s].j = L.pj[s]; pairs[s].dc = L.pdc[s]; }
+            std::vector<LaneEnt> ents(LL.ent_j.size());
+            for (size_t e = 0; e < ents.size(); e++) { ents[e].dc = LL.ent_dc[e]; ents[e].j = LL.ent_j[e]; ents[e].pad = 0; }
+            std::vector<long long> roff(LL.row_off.begin(), LL.row_off.end());
+            LaneDev &ld = m->ld;
+            ld.nkg = nkg;
+#define UPL(vec, field)                                             \
+    do { rc = upload(m, vec, &ld.field); if (rc) { ehic_model_destroy(m); return rc; } } while (0)
+            UPL(pairs, pairs); UPL(LL.slot_a, slot_a); UPL(LL.slot_b, slot_b); UPL(roff, row_off); UPL(ents, ent);
+#undef UPL
+            m->use_lanes = true;
+            m->n_quads = (N + EHIC_LANE_WARPS - 1) / EHIC_LANE_WARPS;
+        }
+    }
     // free the big host vectors we no longer need
     std::vector<int32_t>().swap(L.ent_j); std::vector<double>().swap(L.ent_dc);
     std::vector<int32_t>().swap(L.slot_a); std::vector<int32_t>().swap(L.slot_b);
     std::vector<double>().swap(L.pdc); std::vector<double>().swap(L.pcnt);
 
-    m->kt = pick_kt(S);
+    m->kt = m->use_lanes ? 32 : pick_kt(S);                  // lane path: xt holds xg[R][nkg][Np][3][32]
     m->nkt = (S + m->kt - 1) / m->kt;
     m->gw = pick_gw(m->nkt);
     m->nktg = (m->nkt + m->gw - 1) / m->gw;
@@ -321,7 +351,7 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     }
     DA(m->partA, Rm * (size_t)std::max(m->nA, 1));
     DA(m->partP, Rm * (size_t)S * m->nPx * 3);
-    DA(m->partK, Rm * (size_t)L.n_slices * m->nktg * m->gw);
+    DA(m->partK, Rm * std::max((size_t)L.n_slices * m->nktg * m->gw, (size_t)m->n_quads * EHIC_LANE_WARPS * m->nkt));
     DA(m->energies, Rm * 4); DA(m->kinetic, Rm);
     if (m->use_tiles) {
         m->nA_tile = m->td.n_tiles;                                   // one forward CTA (partial) per tile
@@ -422,7 +452,7 @@ int ehic_model_info(const ehic_model_t *m, int64_t out[8])
 {
     if (!m || !out) return fail(EHIC_ERR_INVALID, "null argument");
     out[0] = m->dm.N; out[1] = m->dm.S; out[2] = m->dm.M; out[3] = m->max_replicas;
-    out[4] = m->flags; out[5] = m->dm.tot; out[6] = m->device; out[7] = m->kt * 100 + m->gw + (m->use_tiles ? 10000 : 0);
+    out[4] = m->flags; out[5] = m->dm.tot; out[6] = m->device; out[7] = m->kt * 100 + m->gw + (m->use_tiles ? 10000 : 0) + (m->use_lanes ? 20000 : 0);
     return EHIC_OK;
 }
 
@@ -442,7 +472,14 @@ static int launch_pack(ehic_model *m, int R, const double *d_x, double *xs, doub
 {
     long long rows = (long long)R * m->dm.S, total = rows * m->dm.Np;
     KernelTimer kt_(m, KC_PACK, st);
-    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_x, xs, xt, m->dm.N, m->dm.Np, m->dm.S, m->kt, m->nkt, rows);
+    if (m->use_lanes && xt) {
+        dim3 grid((unsigned)(m->dm.Np / 32), (unsigned)m->ld.nkg, (unsigned)R);
+        pack_lane_kernel<<<grid, 256, 0, st>>>(d_x, xs, xt, m->dm.N, m->dm.Np, m->dm.S, m->ld.nkg);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        return EHIC_OK;
+    }
+    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_x, xs, xt, m->dm.N, m->dm.Np, m->dm.S, m->kt, m->nkt, rows, m->use_lanes ? 1 : 0);
     LAUNCHED();
     CU(cudaGetLastError());
     return EHIC_OK;
@@ -470,6 +507,13 @@ static int launch_forward(ehic_model *m, int R, const double *xs, const double *
         return EHIC_OK;
     }
     dim3 grid((unsigned)m->nA, (unsigned)R);
+    if (m->use_lanes) {
+        forward_lane_kernel<<<grid, 256, 0, st>>>(m->dm, m->ld, m->xt[m->cur_xt], d_norm, d_md, want_w ? m->wbuf : nullptr,
+                                                   m->partA, want_logl);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        return EHIC_OK;
+    }
     static const bool fwd_soa = []() { const char *e = getenv("EHIC_FORWARD"); return e && !strcmp(e, "soa"); }();
     if (m->flags & EHIC_FLAG_EXACT)
         forward_kernel<true><<<grid, 256, 0, st>>>(m->dm, xs, d_norm, d_md, want_w ? m->wbuf : nullptr, m->partA, want_logl);
@@ -568,6 +612,13 @@ static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_
         return EHIC_OK;
     }
     KernelTimer kt_(m, KC_GATHER, st);
+    if (m->use_lanes) {
+        const unsigned blocks = (unsigned)((long long)R * m->ld.nkg * m->n_quads);
+        backward_lane_kernel<<<blocks, EHIC_LANE_WARPS * 32, 0, st>>>(m->dm, m->ld, ga, m->n_quads);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        return EHIC_OK;
+    }
     if (m->flags & EHIC_FLAG_EXACT) launch_gather_t<true>(m, ga, R, st);
     else launch_gather_t<false>(m, ga, R, st);
     CU(cudaGetLastError());
@@ -581,7 +632,9 @@ static int launch_finalize(ehic_model *m, int R, bool haveA, bool haveP, bool ha
     finalize_kernel<<<R, 256, 0, st>>>(m->dm, haveA ? m->partA : nullptr, m->use_tiles ? m->nA_tile : m->nA,
                                        haveP ? m->partP : nullptr, (long long)m->dm.S * m->nPx,
                                        haveK ? m->partK : nullptr,
-                                       m->use_tiles ? (long long)m->dm.S * m->nKc : (long long)m->dm.n_slices * m->nktg * m->gw,
+                                       m->use_tiles ? (long long)m->dm.S * m->nKc
+                                       : m->use_lanes ? (long long)m->ld.nkg * m->n_quads * EHIC_LANE_WARPS
+                                                      : (long long)m->dm.n_slices * m->nktg * m->gw,
                                        (haveP && m->last_prior_used_cells) ? m->partC : nullptr, m->dm.S,
                                        d_energies, d_kin);
     LAUNCHED();

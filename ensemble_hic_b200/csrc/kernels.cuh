@@ -109,8 +109,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 // xt ("tile-AoS") is the gather kernel's copy: one record holds bead o of the KT structures of
 // one structure tile (KT*24 B, contiguous), so a partner costs one address computation and
 // KT*3/2 LDG.128 instead of KT*3 separately addressed LDG.64.
+//
+// With `lanes` set, xt is the LANE layout of the sparse path instead: xg[R][nkg][Np][3][32], one
+// structure per lane (KT = 32, nkt = nkg), so a warp reads one bead of 32 structures as three
+// fully coalesced 256-byte rows.
 __global__ void pack_kernel(const double *__restrict__ x, double *__restrict__ xs, double *__restrict__ xt,
-                            int N, int Np, int S, int KT, int nkt, long long rows /* R*S */)
+                            int N, int Np, int S, int KT, int nkt, long long rows /* R*S */, int lanes)
 {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = rows * Np;
@@ -127,8 +131,41 @@ __global__ void pack_kernel(const double *__restrict__ x, double *__restrict__ x
     if (xt && i < N) {
         long long r = row / S;
         int k = (int)(row - r * S);
-        double *u = xt + (((r * nkt + k / KT) * Np + i) * KT + (k % KT)) * 3;
-        u[0] = a; u[1] = b; u[2] = c;
+        if (lanes) {
+            double *u = xt + ((r * nkt + k / 32) * Np + i) * 96 + (k % 32);
+            u[0] = a; u[32] = b; u[64] = c;
+        } else {
+            double *u = xt + (((r * nkt + k / KT) * Np + i) * KT + (k % KT)) * 3;
+            u[0] = a; u[1] = b; u[2] = c;
+        }
+    }
+}
+
+// Lane layout of the sparse path: x[R][S][N][3] -> xs[R][S][3][Np] and xg[R][nkg][Np][3][32] (structure <-> lane).
+// A 32-structure x 32-bead tile goes through shared memory so that both the reads (96 consecutive
+// doubles per structure) and the writes (96 consecutive doubles per bead) are coalesced; padding
+// structures and beads are written as zeros.
+__global__ void __launch_bounds__(256)
+pack_lane_kernel(const double *__restrict__ x, double *__restrict__ xs, double *__restrict__ xg,
+                 int N, int Np, int S, int nkg)
+{
+    __shared__ double t[32][97];
+    const int i0 = blockIdx.x * 32, kg = blockIdx.y, r = blockIdx.z;
+    for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
+        const int k = idx / 96, q = idx - k * 96;
+        const int kgl = kg * 32 + k;
+        const long long col = 3LL * i0 + q;
+        double v = 0.0;
+        if (kgl < S && col < 3LL * N) v = x[((long long)r * S + kgl) * N * 3 + col];
+        t[k][q] = v;
+    }
+    __syncthreads();
+    double *g = xg + (((long long)r * nkg + kg) * Np + i0) * 96;
+    for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) g[idx] = t[idx & 31][idx >> 5];
+    for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
+        const int b = idx & 31, kc = idx >> 5, k = kc / 3, c = kc - 3 * k;
+        const int kgl = kg * 32 + k;
+        if (kgl < S) xs[(((long long)r * S + kgl) * 3 + c) * Np + i0 + b] = t[k][3 * b + c];
     }
 }
 
@@ -944,6 +981,203 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
     if (ga.partK) {
         kin = warp_sum(kin);
         if (lane == 0) ga.partK[(long long)blockIdx.x * n_warps + warp] = kin;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// LANE path (large sparse contact lists, fast arithmetic): lane <-> structure.
+//
+// A warp works on ONE bead pair for the 32 structures of a structure group at a time, so the pair's
+// metadata (partner index, contact distance, weight) is warp-uniform (broadcast loads), the
+// coordinates of a bead are three coalesced 256-byte rows of xg[R][nkg][Np][3][32] however scattered
+// the list is, and the ensemble reduction of the forward model is a warp shuffle reduction.  (The
+// row path reads one 24*KT-byte record per lane: 32 different cache lines per load instruction,
+// which leaves it L1-wavefront / L2-sector bound on large sparse lists,
+// profiles/r01_sparse_rowpath_E.txt.)  On lists without locality the bound is the L2 -> SM fabric
+// (24 bytes per pair and structure), not the FP64 pipe.  Tried and rejected: moving every 768-byte
+// partner row with its own TMA bulk copy (the per-copy cost of the TMA unit makes it 3x slower than
+// plain coalesced loads) and L1 prefetch instructions (slower).
+// No atomics; every output has one writer and a fixed order.
+struct __align__(16) LanePair { int i, j; double dc; };
+struct __align__(16) LaneEnt { double dc; int j; int pad; };
+
+struct LaneDev {
+    int nkg;                        // structure groups of 32 lanes
+    const LanePair *pairs;          // [M]  (i, j)-sorted pair view
+    const int *slot_a, *slot_b;     // [M]  CSR positions of (i -> j) and (j -> i)
+    const long long *row_off;       // [N+1] CSR: both directions of every pair
+    const LaneEnt *ent;             // [2M]
+};
+
+__device__ __forceinline__ void reduce8(double (&r)[8], int lane);      // defined with the tile kernels below
+
+// Forward, lane form: CTA <-> 256 consecutive pairs of the sorted list (8 warps x 32 pairs), in
+// batches of 8 pairs per warp: the 8 per-lane sums over the structure groups are reduced across the
+// warp with ONE halving butterfly (reduce8) per batch, and after 4 batches every lane finishes one
+// pair (mock count, Poisson weight into both CSR slots, log-likelihood term).  Bead i of
+// consecutive pairs is the same most of the time and stays in registers.
+#ifndef EHIC_LANE_FWD_MINB
+#define EHIC_LANE_FWD_MINB 3
+#endif
+#ifndef EHIC_LANE_UNROLL
+#define EHIC_LANE_UNROLL 8
+#endif
+constexpr int kLaneUnroll = EHIC_LANE_UNROLL;
+__global__ void __launch_bounds__(256, EHIC_LANE_FWD_MINB)
+forward_lane_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, const double *__restrict__ norm,
+                    double *__restrict__ md_out, double *__restrict__ wbuf,
+                    double *__restrict__ partA, int want_logl)
+{
+    const int r = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long m0 = ((long long)blockIdx.x * 8 + warp) * 32;
+    const double nrm = norm[r], alpha = dm.alpha;
+    const long long gstride = (long long)dm.Np * 96;
+    const double *xr = xg + (long long)r * ld.nkg * gstride + lane;
+    double term = 0.0;
+    if (m0 < dm.M) {                                    // warp-uniform
+        double tot[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const long long mb = m0 + b * 8;
+            if (mb < dm.M) {                            // warp-uniform
+                double acc[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) acc[e] = 0.0;
+                for (int kg = 0; kg < ld.nkg; kg++) {
+                    const double *xk = xr + kg * gstride;
+                    const bool kv = kg * 32 + lane < dm.S;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+                    int ci = -1;
+                    LanePair pr[8];                     // re-read per structure group (L1-resident broadcast loads)
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int4 v = __ldg(reinterpret_cast<const int4 *>(ld.pairs + min(mb + e, dm.M - 1)));
+                        pr[e].i = v.x; pr[e].j = v.y; pr[e].dc = __hiloint2double(v.w, v.z);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        if (pr[e].i != ci) {            // warp-uniform
+                            ci = pr[e].i;
+                            const double *p = xk + (long long)ci * 96;
+                            a0 = p[0]; a1 = p[32]; a2 = p[64];
+                        }
+                        const double *q = xk + (long long)pr[e].j * 96;
+                        const double dx = a0 - q[0], dy = a1 - q[32], dz = a2 - q[64];
+                        const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                        const double rd = rsqrt_nr(s2);
+                        const double tt = alpha * (pr[e].dc - s2 * rd);
+                        const double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                        const double sv = fma(tt, rq, 1.0);
+                        acc[e] += kv ? sv : 0.0;
+                    }
+                }
+                reduce8(acc, lane);                     // lane L holds the total of pair mb + (L >> 2)
+                tot[b] = acc[0];
+            }
+        }
+        // lane L finishes pair m0 + 8 (L & 3) + (L >> 2)
+        const int bsel = lane & 3;
+        const double sum = bsel == 0 ? tot[0] : (bsel == 1 ? tot[1] : (bsel == 2 ? tot[2] : tot[3]));
+        const long long m = m0 + 8 * bsel + (lane >> 2);
+        if (m < dm.M) {
+            const double c = dm.pcnt[m];
+            const double md = sum * (0.5 * nrm);
+            if (md_out) md_out[(long long)r * dm.M + dm.perm[m]] = md;
+            const double em = __dsub_rn(1.0, __ddiv_rn(c, md));
+            const double w = __dmul_rn(__dmul_rn(__dmul_rn(0.5, em), nrm), alpha);
+            if (wbuf) {
+                double *wr = wbuf + (long long)r * dm.wstride;
+                wr[ld.slot_a[m]] = w;
+                wr[ld.slot_b[m]] = w;
+            }
+            if (want_logl) term = c * log(md) - md;
+        }
+    }
+    if (want_logl) {
+        __shared__ double sh[8];
+        double v = warp_sum(term);
+        if (lane == 0) sh[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            partA[(long long)r * gridDim.x + blockIdx.x] = ((sh[0] + sh[1]) + (sh[2] + sh[3])) + ((sh[4] + sh[5]) + (sh[6] + sh[7]));
+    }
+}
+
+// Backward, lane form: warp <-> (replica, structure group, bead b); lane <-> structure.  The warp
+// walks the CSR row of b -- (partner, contact distance) and the weight are broadcast loads, the
+// partner's coordinates three coalesced rows -- and accumulates g_b of its 32 structures in
+// registers: a gather, every pair evaluated from both ends, no atomics, fixed order.  CTA = 4
+// consecutive beads of one structure group, so neighbouring rows share partner lines in L1.
+// Epilogue as in gather_kernel (lammda * g + priors, optional leapfrog kick + drift).
+#define EHIC_LANE_WARPS 4
+__global__ void __launch_bounds__(EHIC_LANE_WARPS * 32)
+backward_lane_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int quad = blockIdx.x % n_quads;
+    const int tmp = blockIdx.x / n_quads;
+    const int kg = tmp % ld.nkg;
+    const int r = tmp / ld.nkg;
+    const int b = quad * EHIC_LANE_WARPS + warp;
+    const bool bead_ok = b < dm.N;
+    const int bb = bead_ok ? b : dm.N - 1;
+    const int k = kg * 32 + lane;
+    const bool k_ok = k < dm.S;
+    const long long gstride = (long long)dm.Np * 96;
+    const double *xk = ga.xt + ((long long)r * ld.nkg + kg) * gstride + lane;
+    const double x0 = xk[(long long)bb * 96], x1 = xk[(long long)bb * 96 + 32], x2 = xk[(long long)bb * 96 + 64];
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    if (ga.contact && dm.M > 0 && bead_ok) {            // warp-uniform
+        const long long e0 = ld.row_off[b], e1 = ld.row_off[b + 1];
+        const double *wr = ga.wbuf + (long long)r * dm.wstride;
+        const double alpha = dm.alpha;
+#pragma unroll kLaneUnroll
+        for (long long e = e0; e < e1; e++) {
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(ld.ent + e));
+            const double dc = __hiloint2double(v.y, v.x);
+            const double w = wr[e];
+            const double *q = xk + (long long)v.z * 96;
+            const double dx = q[0] - x0, dy = q[32] - x1, dz = q[64] - x2;
+            const double s = fma(dz, dz, fma(dy, dy, dx * dx));
+            const double rd = rsqrt_nr(s);
+            const double tt = alpha * (dc - s * rd);
+            const double rq = rsqrt_nr(fma(tt, tt, 1.0));
+            const double f = w * ((rq * rq) * (rq * rd));
+            acc0 = fma(f, dx, acc0);
+            acc1 = fma(f, dy, acc1);
+            acc2 = fma(f, dz, acc2);
+        }
+    }
+    const double lam = ga.lammda ? ga.lammda[r] : 1.0;
+    double kin = 0.0;
+    if (k_ok && bead_ok) {
+        const long long at = (((long long)r * dm.S + k) * dm.N + b) * 3;
+        double g0 = __dmul_rn(lam, acc0), g1 = __dmul_rn(lam, acc1), g2 = __dmul_rn(lam, acc2);
+        if (ga.gprior) {
+            g0 = __dadd_rn(g0, ga.gprior[at]); g1 = __dadd_rn(g1, ga.gprior[at + 1]); g2 = __dadd_rn(g2, ga.gprior[at + 2]);
+        }
+        if (ga.grad) { ga.grad[at] = g0; ga.grad[at + 1] = g1; ga.grad[at + 2] = g2; }
+        if (ga.p) {
+            const double eps = ga.eps[r];
+            double p0 = ga.p[at], p1 = ga.p[at + 1], p2 = ga.p[at + 2];
+            if (ga.kinetic_mode == 1) kin += p0 * p0 + p1 * p1 + p2 * p2;
+            const double ke = ga.kick * eps;
+            p0 = fma(-ke, g0, p0); p1 = fma(-ke, g1, p1); p2 = fma(-ke, g2, p2);
+            ga.p[at] = p0; ga.p[at + 1] = p1; ga.p[at + 2] = p2;
+            if (ga.kinetic_mode == 2) kin += p0 * p0 + p1 * p1 + p2 * p2;
+            if (ga.xs_next) {
+                const double n0 = fma(eps, p0, x0), n1 = fma(eps, p1, x1), n2 = fma(eps, p2, x2);
+                double *xn = ga.xs_next + ((long long)r * dm.S + k) * 3LL * dm.Np;
+                xn[b] = n0; xn[dm.Np + b] = n1; xn[2 * dm.Np + b] = n2;
+                double *un = ga.xt_next + ((long long)r * ld.nkg + kg) * gstride + (long long)b * 96 + lane;
+                un[0] = n0; un[32] = n1; un[64] = n2;
+            }
+        }
+    }
+    if (ga.partK) {
+        kin = warp_sum(kin);
+        if (lane == 0) ga.partK[(long long)blockIdx.x * EHIC_LANE_WARPS + warp] = kin;
     }
 }
 

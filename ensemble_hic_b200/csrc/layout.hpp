@@ -236,4 +236,35 @@ inline std::string build_layout(int32_t N, int64_t M, const int64_t *data, const
     return "";
 }
 
+// (4) LANE view (sparse lists, fast arithmetic): the kernels put the 32 structures of a structure
+//     group on the 32 lanes of a warp, so everything about a pair is warp-uniform and the list is
+//     plain CSR: row_off[b] .. row_off[b+1] are bead b's entries (partner, contact distance), both
+//     directions of every pair present; slot_a[m] / slot_b[m] are the CSR positions of sorted pair m
+//     in row i and in row j (where the forward kernel drops the pair's weight).
+struct LaneLayout {
+    std::vector<int64_t> row_off;          // N + 1
+    std::vector<int32_t> ent_j;            // 2 M
+    std::vector<double> ent_dc;            // 2 M
+    std::vector<int32_t> slot_a, slot_b;   // M
+};
+
+inline std::string build_lanes(const ContactLayout &L, LaneLayout &C)
+{
+    C = LaneLayout();
+    const int32_t N = L.N; const int64_t M = L.M;
+    if (2 * M >= ((int64_t)1 << 31)) return "contact list too large for 32-bit row slots";
+    C.row_off.assign((size_t)N + 1, 0);
+    for (int32_t b = 0; b < N; b++) C.row_off[b + 1] = C.row_off[b] + L.row_len[b];
+    C.ent_j.resize((size_t)2 * M); C.ent_dc.resize((size_t)2 * M);
+    C.slot_a.resize(M); C.slot_b.resize(M);
+    std::vector<int64_t> fill(C.row_off.begin(), C.row_off.end() - 1);
+    for (int64_t s = 0; s < M; s++) {
+        const int32_t i = L.pi[s], j = L.pj[s];
+        int64_t a = fill[i]++, b = fill[j]++;
+        C.ent_j[a] = j; C.ent_dc[a] = L.pdc[s]; C.slot_a[s] = (int32_t)a;
+        C.ent_j[b] = i; C.ent_dc[b] = L.pdc[s]; C.slot_b[s] = (int32_t)b;
+    }
+    return "";
+}
+
 }  // namespace ehic

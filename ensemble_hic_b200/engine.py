@@ -103,8 +103,9 @@ class Model(object):
     def info(self):
         out = (C.c_int64 * 8)()
         _lib.check(self._L.ehic_model_info(self._h, out))
+        path = "lanes" if out[7] >= 20000 else ("tiles" if out[7] >= 10000 else "rows")
         return dict(N=out[0], S=out[1], M=out[2], max_replicas=out[3], flags=out[4], slots=out[5],
-                    device=out[6], kt=out[7])
+                    device=out[6], kt=out[7], path=path)
 
     # ---- per-kernel timing ------------------------------------------------------------------
     KERNEL_CLASSES = ("pack", "forward", "prior", "gather", "finalize", "other")

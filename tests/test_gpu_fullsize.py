@@ -41,7 +41,7 @@ def test_config_d_paths_and_modes_agree(cfg_d):
     """tile path == row path == exact (reference-order, IEEE) arithmetic at full size"""
     pb = cfg_d
     tiles, rows, exact = _model(pb), _model(pb, path="rows"), _model(pb, exact=True)
-    assert tiles.info()["kt"] >= 10000 and rows.info()["kt"] < 10000
+    assert tiles.info()["path"] == "tiles" and rows.info()["path"] != "tiles"
     out = {}
     for name, m in (("tiles", tiles), ("rows", rows), ("exact", exact)):
         out[name] = m.evaluate(pb["X"], 3.0, 0.7, 0.4, energies=True, md=True)
@@ -114,11 +114,12 @@ def test_config_d_trajectory_is_reversible(cfg_d):
     m.close()
 
 
-def test_config_e_shape_sparse_list():
-    """10 000 beads, sparse list drawn with P(i, j) ~ 1/|i-j|, 8 structures"""
+@pytest.mark.parametrize("S,path", [(8, "rows"), (32, "lanes")])
+def test_config_e_shape_sparse_list(S, path):
+    """10 000 beads, sparse list drawn with P(i, j) ~ 1/|i-j|, 8 / 32 structures"""
     from ensemble_hic_b200.engine import Model
     rng = np.random.default_rng(3)
-    N, S, M = 10000, 8, 400000
+    N, M = 10000, 400000
     sep = np.minimum((np.exp(rng.uniform(np.log(2), np.log(N - 1), size=3 * M))).astype(np.int64), N - 1)
     i = rng.integers(0, N, size=3 * M); j = i + sep
     ok = j < N
@@ -129,7 +130,7 @@ def test_config_e_shape_sparse_list():
     X = random_walk(rng, S, N, 0.9)
     fast = Model(S, radii, data, cds, alpha=10.0, k_nb=500.0, k_bb=500.0)
     exact = Model(S, radii, data, cds, alpha=10.0, k_nb=500.0, k_bb=500.0, exact=True)
-    assert fast.info()["kt"] < 10000                    # sparse: row path
+    assert fast.info()["path"] == path                       # sparse: row path, or lane path when S fills the warps
     a = fast.evaluate(X, 3.0, 0.7, 0.4, energies=True, md=True)
     b = exact.evaluate(X, 3.0, 0.7, 0.4, energies=True, md=True)
     assert relerr(a["grad"], b["grad"]) < 1e-12 and relerr(a["md"], b["md"]) < 1e-12

@@ -219,7 +219,7 @@ def test_tile_path_matches_oracle(co, monkeypatch, S, N, density, min_sep):
     X = np.stack([pb["X"] + rng.normal(scale=0.03, size=pb["X"].shape) for _ in range(R)])
     norm = rng.uniform(1, 5, R); lam = np.array([0.2, 1.0, 0.6]); bet = np.array([1.0, 0.3, 0.0])
     m = _model(pb, False, max_replicas=R)
-    assert m.info()["kt"] >= 10000, "tile path not selected"
+    assert m.info()["path"] == "tiles", "tile path not selected"
     out = m.evaluate(X, norm, lam, bet, energies=True, md=True)
     for r in range(R):
         assert relerr(out["md"][r], op.mock_data(X[r], norm[r])) < FAST_TOL
@@ -230,7 +230,7 @@ def test_tile_path_matches_oracle(co, monkeypatch, S, N, density, min_sep):
     assert relerr(glik, co.calculate_gradient(X[0], pb["alpha"], norm[0], pb["cds"], pb["data"])) < FAST_TOL
     monkeypatch.setenv("EHIC_PATH", "rows")                      # the two GPU paths agree with each other
     m2 = _model(pb, False, max_replicas=R)
-    assert m2.info()["kt"] < 10000
+    assert m2.info()["path"] != "tiles"
     out2 = m2.evaluate(X, norm, lam, bet, md=True)
     assert relerr(out["grad"], out2["grad"]) < 1e-13 and relerr(out["md"], out2["md"]) < 1e-13
 
@@ -239,13 +239,13 @@ def test_tile_path_is_chosen_for_dense_lists_only(monkeypatch):
     monkeypatch.delenv("EHIC_PATH", raising=False)
     dense = make_problem(seed=3, S=2, N=256, density=1.0)
     sparse = make_problem(seed=3, S=2, N=256, density=0.1)
-    assert _model(dense, False).info()["kt"] >= 10000
-    assert _model(sparse, False).info()["kt"] < 10000
-    assert _model(dense, True).info()["kt"] < 10000           # exact mode keeps the row path (reference order)
+    assert _model(dense, False).info()["path"] == "tiles"
+    assert _model(sparse, False).info()["path"] != "tiles"
+    assert _model(dense, True).info()["path"] != "tiles"           # exact mode keeps the row path (reference order)
     dup = dict(dense)
     dup["data"] = np.concatenate([dense["data"], dense["data"][:1][:, [1, 0, 2]]])     # (j, i) duplicate of a pair
     dup["cds"] = np.concatenate([dense["cds"], dense["cds"][:1]])
-    assert _model(dup, False).info()["kt"] < 10000
+    assert _model(dup, False).info()["path"] != "tiles"
 
 
 def test_tile_path_trajectory(co, monkeypatch):
@@ -264,7 +264,7 @@ def test_tile_path_trajectory(co, monkeypatch):
     P = rng.normal(size=X.shape)
     norm = np.array([2.5, 3.5]); lam = np.array([0.3, 1.0]); bet = np.array([0.5, 1.0]); eps = np.array([5e-4, 1e-3])
     m = _model(pb, False, max_replicas=R)
-    assert m.info()["kt"] >= 10000
+    assert m.info()["path"] == "tiles"
     dev = torch.device("cuda:0")
     t = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
     x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
@@ -276,6 +276,83 @@ def test_tile_path_trajectory(co, monkeypatch):
         assert relerr(x_t[r].cpu().numpy(), x1) < 1e-11 and relerr(p_t[r].cpu().numpy(), p1) < 1e-9
         E1 = -op.log_prob(x1, norm[r], lam[r], bet[r])
         assert abs(H[r, 2] - E1) <= 1e-10 * abs(E1)
+        assert abs(H[r, 3] - 0.5 * np.sum(p1 ** 2)) <= 1e-9 * H[r, 3]
+
+
+# ---- lane path (sparse lists, fast mode: lane <-> structure) -------------------------------------------
+
+@pytest.mark.parametrize("S,N,density,min_sep", [(30, 64, 0.3, 1), (33, 50, 0.5, 1), (64, 40, 1.0, 1), (20, 100, 0.1, 2),
+                                                 (1, 30, 0.5, 1), (100, 37, 0.6, 1), (32, 200, 0.02, 3)])
+def test_lane_path_matches_oracle(co, monkeypatch, S, N, density, min_sep):
+    from oracle.oracle import OraclePosterior
+    from ensemble_hic_b200.engine import TERM_ALL
+    monkeypatch.setenv("EHIC_PATH", "lanes")
+    pb = make_problem(seed=S * 1000 + N, S=S, N=N, density=density, min_sep=min_sep, uniform_radii=False, step=0.7)
+    ul = pb["radii"][:-1] + pb["radii"][1:]
+    op = OraclePosterior(S, pb["data"], pb["cds"], pb["alpha"], pb["radii"], 50.0, 500.0,
+                         [np.zeros(N - 1)], [ul], [0, N], nonbonded="n2")
+    R = 3
+    rng = np.random.default_rng(1)
+    X = np.stack([pb["X"] + rng.normal(scale=0.03, size=pb["X"].shape) for _ in range(R)])
+    norm = rng.uniform(1, 5, R); lam = np.array([0.2, 1.0, 0.6]); bet = np.array([1.0, 0.3, 0.0])
+    m = _model(pb, False, max_replicas=R)
+    assert m.info()["path"] == "lanes", "lane path not selected"
+    out = m.evaluate(X, norm, lam, bet, energies=True, md=True)
+    for r in range(R):
+        assert relerr(out["md"][r], op.mock_data(X[r], norm[r])) < FAST_TOL
+        assert relerr(out["grad"][r], op.gradient(X[r], norm[r], lam[r], bet[r])) < FAST_TOL
+        E = op.energies(X[r], norm[r])
+        assert abs(out["energies"][r, 0] - E[0]) <= 1e-11 * abs(E[0])
+    glik = m.evaluate(X[0], norm[0], terms=1)["grad"][0]
+    assert relerr(glik, co.calculate_gradient(X[0], pb["alpha"], norm[0], pb["cds"], pb["data"])) < FAST_TOL
+    gprior = m.evaluate(X[0], norm[0], terms=TERM_ALL & ~1)["grad"][0]       # no contact term: epilogue only
+    assert relerr(gprior, op.gradient(X[0], norm[0], 0.0, 1.0)) < FAST_TOL
+    monkeypatch.setenv("EHIC_PATH", "rows")                      # the two GPU paths agree with each other
+    m2 = _model(pb, False, max_replicas=R)
+    assert m2.info()["path"] == "rows"
+    out2 = m2.evaluate(X, norm, lam, bet, md=True)
+    assert relerr(out["grad"], out2["grad"]) < 1e-13 and relerr(out["md"], out2["md"]) < 1e-13
+
+
+def test_lane_path_is_chosen_for_sparse_lists_with_enough_structures(monkeypatch):
+    monkeypatch.delenv("EHIC_PATH", raising=False)
+    assert _model(make_problem(seed=3, S=30, N=256, density=0.1), False).info()["path"] == "lanes"
+    assert _model(make_problem(seed=3, S=40, N=64, density=0.1), False).info()["path"] == "lanes"     # 40 of 64 lanes
+    assert _model(make_problem(seed=3, S=36, N=64, density=0.1), False).info()["path"] == "rows"      # 36 of 64 lanes
+    assert _model(make_problem(seed=3, S=2, N=256, density=0.1), False).info()["path"] == "rows"
+    assert _model(make_problem(seed=3, S=30, N=256, density=0.1), True).info()["path"] == "rows"      # exact: reference order
+    assert _model(make_problem(seed=3, S=30, N=256, density=1.0), False).info()["path"] == "tiles"
+
+
+def test_lane_path_trajectory(co, monkeypatch):
+    import torch
+    from oracle.oracle import OraclePosterior, leapfrog
+    monkeypatch.setenv("EHIC_PATH", "lanes")
+    monkeypatch.setenv("EHIC_TRAJ", "multi")          # the multi-kernel (CUDA graph) trajectory, not the one-CTA kernel
+    pb = make_problem(seed=78, S=35, N=61, density=0.3, step=0.8)
+    N, S = pb["N"], pb["S"]
+    ul = pb["radii"][:-1] + pb["radii"][1:]
+    op = OraclePosterior(S, pb["data"], pb["cds"], pb["alpha"], pb["radii"], 50.0, 500.0,
+                         [np.zeros(N - 1)], [ul], [0, N], nonbonded="n2")
+    R, L = 2, 6
+    rng = np.random.default_rng(0)
+    X = np.stack([pb["X"], pb["X"] + rng.normal(scale=0.05, size=pb["X"].shape)]).reshape(R, -1)
+    P = rng.normal(size=X.shape)
+    norm = np.array([2.5, 3.5]); lam = np.array([0.3, 1.0]); bet = np.array([0.5, 1.0]); eps = np.array([5e-4, 1e-3])
+    m = _model(pb, False, max_replicas=R)
+    assert m.info()["path"] == "lanes"
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
+    m.hmc_trajectory_device(R, L, x_t, p_t, t(norm), t(lam), t(bet), t(eps), H_t)
+    torch.cuda.synchronize()
+    H = H_t.cpu().numpy()
+    for r in range(R):
+        x1, p1 = leapfrog(lambda x: op.gradient(x, norm[r], lam[r], bet[r]), X[r], P[r], eps[r], L)
+        assert relerr(x_t[r].cpu().numpy(), x1) < 1e-11 and relerr(p_t[r].cpu().numpy(), p1) < 1e-9
+        E0 = -op.log_prob(X[r], norm[r], lam[r], bet[r]); E1 = -op.log_prob(x1, norm[r], lam[r], bet[r])
+        assert abs(H[r, 0] - E0) <= 1e-10 * abs(E0) and abs(H[r, 2] - E1) <= 1e-10 * abs(E1)
+        assert abs(H[r, 1] - 0.5 * np.sum(P[r] ** 2)) <= 1e-12 * H[r, 1]
         assert abs(H[r, 3] - 0.5 * np.sum(p1 ** 2)) <= 1e-9 * H[r, 3]
 
 

@@ -14,4 +14,4 @@ for (S, N, dens) in ((5, 70, 1.0), (3, 300, 1.0), (9, 100, 0.2)):
     nb = m.evaluate(pb["X"], 3.3, terms=2)["grad"][0]
     gn = np.concatenate([co.forcefield_gradient(x, pb["radii"], pb["radii"] ** 2, 50.0) for x in pb["X"]])
     print("S=%d N=%d tiles=%s: grad relerr %.2e, md max elementwise rel %.2e, nb grad relerr %.2e"
-          % (S, N, m.info()["kt"] >= 10000, relerr(out["grad"][0], g), np.max(np.abs(out["md"][0] - md) / md), relerr(nb, gn)))
+          % (S, N, m.info()["path"] == "tiles", relerr(out["grad"][0], g), np.max(np.abs(out["md"][0] - md) / md), relerr(nb, gn)))

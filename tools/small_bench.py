@@ -27,5 +27,5 @@ for name, R in (("hairpin_s", 2), ("proteins", 7), ("proteins", 54), ("nora2012"
     for _ in range(n): run()
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / n
     print("%-10s N=%4d S=%3d M=%6d R=%3d tiles=%s: trajectory L=%d %.3f ms  (%.1f us/leapfrog step, %d launches) -> %.0f replica-grad-evals/s"
-          % (name, N, S, len(g["data"]), R, m.info()["kt"] >= 10000, L, dt * 1e3, dt * 1e6 / (L + 1), (launch_count() - l0) // n, R * (L + 1) / dt), flush=True)
+          % (name, N, S, len(g["data"]), R, m.info()["path"] == "tiles", L, dt * 1e3, dt * 1e6 / (L + 1), (launch_count() - l0) // n, R * (L + 1) / dt), flush=True)
     m.close()
