@@ -53,6 +53,9 @@ struct ehic_model {
     bool nb_fused = false;          // tiles cover all bead pairs: nonbonded force rides in the backward tile kernel
     const unsigned char *tile_clean = nullptr;
     TileDev td{};
+    bool f32 = false;               // EHIC_FLAG_FP32: FP32 pair arithmetic in the tile kernels
+    const float *dc32 = nullptr;    // [n_tiles*4096] contact distances as floats
+    float *tw32 = nullptr;          // [R][n_tiles*4096] lammda * weight as floats
     bool use_lanes = false;         // sparse list + fast mode + enough structures to fill warps: lane path
     LaneDev ld{};
     int n_quads = 0;                // lane path: backward CTAs per (replica, structure group)
@@ -198,8 +201,8 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         return fail(EHIC_ERR_INVALID, "data_points / contact_distances missing");
     if (!desc->bead_radii) return fail(EHIC_ERR_INVALID, "bead_radii missing");
     if (desc->max_replicas <= 0) return fail(EHIC_ERR_INVALID, "max_replicas must be positive");
-    if (desc->flags & EHIC_FLAG_FP32)
-        return fail(EHIC_ERR_INVALID, "EHIC_FLAG_FP32 is not available in this build (see DESIGN.md)");
+    if ((desc->flags & EHIC_FLAG_FP32) && (desc->flags & EHIC_FLAG_EXACT))
+        return fail(EHIC_ERR_INVALID, "EHIC_FLAG_FP32 and EHIC_FLAG_EXACT exclude each other");
     int rc = check_device(device);
     if (rc) return rc;
     CU(cudaSetDevice(device));
@@ -255,6 +258,14 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         if (want && desc->n_data > 0) build_tiles(L, desc->data_points, desc->contact_distances, min_fill, TL);
         m->use_tiles = TL.eligible;
         m->tile_fill = TL.fill;
+        if (desc->flags & EHIC_FLAG_FP32) {
+            if (!TL.eligible) {
+                delete m;
+                return fail(EHIC_ERR_INVALID, "EHIC_FLAG_FP32 needs a dense contact list (tile path): " +
+                                              (TL.why.empty() ? std::string("tile path disabled") : TL.why));
+            }
+            m->f32 = true;
+        }
     }
     std::vector<long long> perm(L.perm.begin(), L.perm.end()), soff(L.slice_off.begin(), L.slice_off.end());
 #define UP(vec, field)                                              \
@@ -276,9 +287,13 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         UPT(TL.mask, mask); UPT(TL.dc, dc); UPT(TL.cnt, cnt); UPT(orig, orig);
 #undef UPT
         rc = upload(m, TL.clean, &m->tile_clean); if (rc) { ehic_model_destroy(m); return rc; }
+        if (m->f32) {
+            std::vector<float> dcf(TL.dc.begin(), TL.dc.end());
+            rc = upload(m, dcf, &m->dc32); if (rc) { ehic_model_destroy(m); return rc; }
+        }
         // fusing the nonbonded force into the backward tile kernel is off by default: with slice bounding-box
         // pruning the separate prior kernel is cheaper than the extra registers the fused variant needs
-        { const char *nf = getenv("EHIC_NB_FUSED"); m->nb_fused = TL.covers_all_pairs && nf && !strcmp(nf, "1"); }
+        { const char *nf = getenv("EHIC_NB_FUSED"); m->nb_fused = !m->f32 && TL.covers_all_pairs && nf && !strcmp(nf, "1"); }
     }
     // sparse lists in fast mode take the lane path (lane <-> structure) when the ensemble fills at least
     // 60 % of the lanes of its structure groups; EHIC_PATH=lanes|rows overrides
@@ -364,6 +379,21 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         DA(pk2, Rm * (size_t)std::max<size_t>((size_t)S * m->nKc, (size_t)L.n_slices * m->nktg * m->gw)); m->partK = pk2;
         if (cudaMemset(m->tw, 0, Rm * (size_t)m->td.slots * sizeof(double)) != cudaSuccess) {
             ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed");
+        }
+        if (m->f32) {
+            const size_t nb32 = sizeof(float) * Rm * (size_t)m->td.slots;
+            if (cudaMalloc(&m->tw32, nb32) != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_NOMEM, "cudaMalloc failed"); }
+            m->owned.push_back(m->tw32);
+            cudaError_t e3 = cudaMemset(m->tw32, 0, nb32);
+            const int fsm32 = (int)forward_tile32_smem_bytes(m->kt);
+            if (e3 == cudaSuccess) {
+                switch (m->kt) {
+                case 4: e3 = cudaFuncSetAttribute(forward_tile32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm32); break;
+                case 2: e3 = cudaFuncSetAttribute(forward_tile32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm32); break;
+                default: e3 = cudaFuncSetAttribute(forward_tile32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm32); break;
+                }
+            }
+            if (e3 != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "FP32 mode setup failed"); }
         }
         // both tile kernels use more than the 48 KB of static shared memory
         cudaError_t e1 = cudaFuncSetAttribute(backward_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -479,7 +509,7 @@ static int launch_pack(ehic_model *m, int R, const double *d_x, double *xs, doub
         CU(cudaGetLastError());
         return EHIC_OK;
     }
-    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_x, xs, xt, m->dm.N, m->dm.Np, m->dm.S, m->kt, m->nkt, rows, m->use_lanes ? 1 : 0);
+    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_x, xs, xt, m->dm.N, m->dm.Np, m->dm.S, m->kt, m->nkt, rows, m->use_lanes ? 1 : (m->f32 ? 2 : 0));
     LAUNCHED();
     CU(cudaGetLastError());
     return EHIC_OK;
@@ -495,6 +525,18 @@ static int launch_forward(ehic_model *m, int R, const double *xs, const double *
     KernelTimer kt_(m, KC_FORWARD, st);
     if (m->use_tiles) {
         dim3 gridt((unsigned)m->td.n_tiles, (unsigned)R);
+        if (m->f32) {
+            float *twp32 = want_w ? m->tw32 : nullptr;
+            const size_t sm32 = forward_tile32_smem_bytes(m->kt);
+            switch (m->kt) {
+            case 4: forward_tile32_kernel<4><<<gridt, 256, sm32, st>>>(m->dm, m->td, m->dc32, m->xt[m->cur_xt], d_norm, d_lammda, d_md, twp32, m->partA, want_logl, m->nkt); break;
+            case 2: forward_tile32_kernel<2><<<gridt, 256, sm32, st>>>(m->dm, m->td, m->dc32, m->xt[m->cur_xt], d_norm, d_lammda, d_md, twp32, m->partA, want_logl, m->nkt); break;
+            default: forward_tile32_kernel<1><<<gridt, 256, sm32, st>>>(m->dm, m->td, m->dc32, m->xt[m->cur_xt], d_norm, d_lammda, d_md, twp32, m->partA, want_logl, m->nkt); break;
+            }
+            LAUNCHED();
+            CU(cudaGetLastError());
+            return EHIC_OK;
+        }
         double *twp = want_w ? m->tw : nullptr;
         const size_t sm = forward_tile_smem(m->kt);
         switch (m->kt) {
@@ -586,7 +628,16 @@ static void launch_gather_t(ehic_model *m, const GatherArgs &ga, int R, cudaStre
 static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_t st)
 {
     if (m->use_tiles) {
-        if (ga.contact) {
+        if (ga.contact && m->f32) {
+            KernelTimer kt_(m, KC_GATHER, st);
+            BackwardTile32Args b32{};
+            b32.xs = ga.xs_cur; b32.dc32 = m->dc32; b32.tw32 = m->tw32; b32.Grow = m->Grow; b32.P = m->Pbuf;
+            b32.tile_clean = m->tile_clean; b32.n_kg = (m->dm.S + 3) / 4;
+            const unsigned blocks = (unsigned)((long long)R * m->td.n_rb * b32.n_kg);
+            backward_tile32_kernel<<<blocks, 128, EHIC_BT_STAGES * 2048 * sizeof(float) + 64, st>>>(m->dm, m->td, b32);
+            LAUNCHED();
+            CU(cudaGetLastError());
+        } else if (ga.contact) {
             KernelTimer kt_(m, KC_GATHER, st);
             BackwardTileArgs ba{};
             ba.xs = ga.xs_cur; ba.tw = m->tw; ba.beta = ga.beta; ba.Grow = m->Grow; ba.P = m->Pbuf;
@@ -606,7 +657,7 @@ static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_
         }
         KernelTimer kt2_(m, KC_OTHER, st);
         dim3 grid((unsigned)m->nKc, (unsigned)m->dm.S, (unsigned)R);
-        combine_kernel<<<grid, 256, 0, st>>>(m->dm, m->td, ga, m->Grow, m->Pbuf, ga.contact, m->kt, m->nkt);
+        combine_kernel<<<grid, 256, 0, st>>>(m->dm, m->td, ga, m->Grow, m->Pbuf, ga.contact, m->kt, m->nkt, m->f32 ? 1 : 0);
         LAUNCHED();
         CU(cudaGetLastError());
         return EHIC_OK;

@@ -103,6 +103,35 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
                  "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// FP32 mode: a coordinate is carried as two floats (hi = float(x), lo = float(x - hi)) in the 8 bytes of
+// the double it replaces, so that differences x_i - x_j = (hi_i - hi_j) + (lo_i - lo_j) keep a relative
+// error of ~1e-7 however far the beads are from the origin.
+__device__ __forceinline__ double split_hilo(double x)
+{
+    const float hi = __double2float_rn(x);
+    const float lo = __double2float_rn(x - (double)hi);
+    return __hiloint2double(__float_as_int(lo), __float_as_int(hi));      // memory order: (hi, lo)
+}
+__device__ __forceinline__ float rsqrt_f32(float x)
+{   // MUFU.RSQ + one Newton step: relative error ~1e-7
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    const float e = fmaf(-x * y, y, 1.0f);
+    return fmaf(0.5f * y, e, y);
+}
+__device__ __forceinline__ float rsqrt_f32_raw(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_f32_raw(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // ---------------------------------------------------------------------------------------
 // x[R][S][N][3] -> xs[R][S][3][Np]  and  xt[R][nkt][Np][KT][3]
 //
@@ -114,8 +143,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 // structure per lane (KT = 32, nkt = nkg), so a warp reads one bead of 32 structures as three
 // fully coalesced 256-byte rows.
 __global__ void pack_kernel(const double *__restrict__ x, double *__restrict__ xs, double *__restrict__ xt,
-                            int N, int Np, int S, int KT, int nkt, long long rows /* R*S */, int lanes)
-{
+                            int N, int Np, int S, int KT, int nkt, long long rows /* R*S */, int mode)
+{   // mode 0: tile-AoS doubles; 1: lane layout; 2: tile-AoS (hi, lo) float pairs of the FP32 mode
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = rows * Np;
     if (t >= total) return;
@@ -131,11 +160,12 @@ __global__ void pack_kernel(const double *__restrict__ x, double *__restrict__ x
     if (xt && i < N) {
         long long r = row / S;
         int k = (int)(row - r * S);
-        if (lanes) {
+        if (mode == 1) {
             double *u = xt + ((r * nkt + k / 32) * Np + i) * 96 + (k % 32);
             u[0] = a; u[32] = b; u[64] = c;
         } else {
             double *u = xt + (((r * nkt + k / KT) * Np + i) * KT + (k % KT)) * 3;
+            if (mode == 2) { a = split_hilo(a); b = split_hilo(b); c = split_hilo(c); }
             u[0] = a; u[1] = b; u[2] = c;
         }
     }
@@ -1605,12 +1635,302 @@ backward_tile_kernel(DevModel dm, TileDev td, BackwardTileArgs ba)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Optional FP32 mode of the tile path (EHIC_FLAG_FP32; north star: 1e-5 relative).  Same mapping,
+// staging and summation structure as the FP64 tile kernels; the pair arithmetic runs on the FP32
+// pipe (128 lanes/clk/SM instead of 64) with MUFU.RSQ reciprocal square roots:
+//   * coordinates are (hi, lo) float pairs (split_hilo), differences formed as (hi-hi) + (lo-lo);
+//   * contact distances and weights are staged as floats (dc32 static, tw32 written by the forward);
+//   * the smooth contact function of far-apart pairs (t < 0) is evaluated as
+//     0.5 / (q^2 (1 + |t|/q)) instead of 0.5 (1 + t/q): no cancellation, so mock counts stay
+//     relatively accurate where FP32 would otherwise lose every digit;
+//   * per-column sums over the ensemble stay in FP32 (S terms); force accumulators are flushed
+//     into FP64 after every tile (128 pairs per lane).
+// Inputs, outputs, weights of the Poisson term, energies and the priors stay FP64.
+template <typename T>
+__device__ __forceinline__ void reduce8_t(T (&r)[8], int lane)
+{
+    bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        T send = hi ? r[i] : r[i + 4], keep = hi ? r[i + 4] : r[i];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    hi = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        T send = hi ? r[i] : r[i + 2], keep = hi ? r[i + 2] : r[i];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    hi = (lane & 4) != 0;
+    {
+        T send = hi ? r[0] : r[1], keep = hi ? r[1] : r[0];
+        r[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    r[0] += __shfl_xor_sync(0xffffffffu, r[0], 2);
+    r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+}
+
+static __host__ __device__ constexpr size_t forward_tile32_smem_bytes(int kt)
+{
+    return 4096 * sizeof(float) + sizeof(double) * ((size_t)EHIC_FT_STAGES * (128 + 32) * kt * 3) + 64;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256, 3)
+forward_tile32_kernel(DevModel dm, TileDev td, const float *__restrict__ dc32, const double *__restrict__ xt,
+                      const double *__restrict__ norm, const double *__restrict__ lammda,
+                      double *__restrict__ md_out, float *__restrict__ tw32,
+                      double *__restrict__ partA, int want_logl, int nkt)
+{
+    constexpr int QC = 16;
+    constexpr int REC = KT * 3;                       // (hi, lo) pairs per record
+    extern __shared__ __align__(16) double smem[];
+    float *s_dc = reinterpret_cast<float *>(smem);     // [4096]
+    double *s_row = smem + 2048;                       // [STAGES][128 * REC]
+    double *s_col = s_row + EHIC_FT_STAGES * 128 * REC;   // [STAGES][32 * REC]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rb = warp & 3, h = warp >> 2;
+    const int tile = blockIdx.x, r = blockIdx.y;
+    const int I = td.tile_I[tile], B = td.tile_B[tile];
+    const int Np = dm.Np;
+    const int row0 = 128 * I, col0 = 32 * B;
+    const double *recs = xt + (long long)r * nkt * Np * REC;
+    const unsigned mask = td.mask[((long long)tile * 4 + rb) * 32 + lane] >> (h * QC);
+    const bool warp_live = __ballot_sync(0xffffffffu, mask != 0u) != 0u;
+    const float alpha = (float)dm.alpha;
+    const int n_row = min(128, Np - row0);
+
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(s_col + EHIC_FT_STAGES * 32 * REC);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q <= EHIC_FT_STAGES; q++) mbar_init(&full[q], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&full[EHIC_FT_STAGES], 4096 * (unsigned)sizeof(float));
+        bulk_g2s(s_dc, dc32 + (long long)tile * 4096, 16384, &full[EHIC_FT_STAGES]);
+    }
+    auto issue = [&](int kt) {
+        if (kt < nkt && threadIdx.x == 0) {
+            const int st = kt % EHIC_FT_STAGES;
+            const double *src_row = recs + ((long long)kt * Np + row0) * REC;
+            const double *src_col = recs + ((long long)kt * Np + col0) * REC;
+            const unsigned row_bytes = (unsigned)(n_row * REC * sizeof(double)), col_bytes = (unsigned)(32 * REC * sizeof(double));
+            mbar_expect_tx(&full[st], row_bytes + col_bytes);
+            bulk_g2s(&s_row[st * 128 * REC], src_row, row_bytes, &full[st]);
+            bulk_g2s(&s_col[st * 32 * REC], src_col, col_bytes, &full[st]);
+        }
+    };
+#pragma unroll
+    for (int c = 0; c < EHIC_FT_STAGES - 1; c++) issue(c);
+    mbar_wait(&full[EHIC_FT_STAGES], 0u);
+
+    float acc[QC];
+#pragma unroll
+    for (int q = 0; q < QC; q++) acc[q] = 0.0f;
+    const int nfull = dm.S / KT;
+    for (int kt = 0; kt < nkt; kt++) {
+        mbar_wait(&full[kt % EHIC_FT_STAGES], (unsigned)((kt / EHIC_FT_STAGES) & 1));
+        __syncthreads();
+        issue(kt + EHIC_FT_STAGES - 1);
+        if (!warp_live) continue;
+        const int st = kt % EHIC_FT_STAGES;
+        const int nvalid = kt < nfull ? KT : dm.S - nfull * KT;
+        float2 own[REC];
+        {
+            const float2 *p = reinterpret_cast<const float2 *>(&s_row[st * 128 * REC + (rb * 32 + lane) * REC]);
+#pragma unroll
+            for (int u = 0; u < REC; u++) own[u] = p[u];
+        }
+        const float2 *pc = reinterpret_cast<const float2 *>(&s_col[st * 32 * REC + h * QC * REC]);
+        const float *pd = &s_dc[(h * QC * 4 + rb) * 32 + lane];
+#pragma unroll
+        for (int q = 0; q < QC; q++) {
+            const float dc = pd[q * 128];
+#pragma unroll
+            for (int t = 0; t < KT; t++) {
+                if (t < nvalid) {                       // warp-uniform; always true except in the last structure tile
+                    const float2 c0 = pc[q * REC + 3 * t], c1 = pc[q * REC + 3 * t + 1], c2 = pc[q * REC + 3 * t + 2];
+                    const float dx = (c0.x - own[3 * t].x) + (c0.y - own[3 * t].y);
+                    const float dy = (c1.x - own[3 * t + 1].x) + (c1.y - own[3 * t + 1].y);
+                    const float dz = (c2.x - own[3 * t + 2].x) + (c2.y - own[3 * t + 2].y);
+                    const float s2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    const float rd = rsqrt_f32(s2);
+                    const float tt = alpha * (dc - s2 * rd);
+                    const float u = fmaf(tt, tt, 1.0f);
+                    const float rq = rsqrt_f32_raw(u);
+                    const float a = fabsf(tt) * rq;      // |t| / q in [0, 1)
+                    const float den = 1.0f + a;
+                    acc[q] += tt >= 0.0f ? den : (rq * rq) * rcp_f32_raw(den);
+                }
+            }
+        }
+    }
+    double term = 0.0;
+    const double nrm = norm[r];
+    const double lam = lammda ? lammda[r] : 1.0;
+    const long long pos0 = (((long long)tile * 32 + h * QC) * 4 + rb) * 32 + lane;
+#pragma unroll
+    for (int q = 0; q < QC; q++) {
+        if ((mask >> q) & 1u) {
+            const long long pos = pos0 + q * 128;
+            const double md = (double)acc[q] * (0.5 * nrm);
+            const double c = td.cnt[pos];
+            if (md_out) md_out[(long long)r * dm.M + td.orig[pos]] = md;
+            if (tw32) {
+                double em = __dsub_rn(1.0, __ddiv_rn(c, md));
+                tw32[(long long)r * td.slots + pos] = (float)(lam * __dmul_rn(__dmul_rn(__dmul_rn(0.5, em), nrm), dm.alpha));
+            }
+            if (want_logl) term += c * log(md) - md;
+        }
+    }
+    if (want_logl) {
+        __shared__ double sh[8];
+        double v = warp_sum(term);
+        if (lane == 0) sh[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            partA[(long long)r * gridDim.x + blockIdx.x] = ((sh[0] + sh[1]) + (sh[2] + sh[3])) + ((sh[4] + sh[5]) + (sh[6] + sh[7]));
+    }
+}
+
+struct BackwardTile32Args {
+    const double *xs;                  // [R][S][3][Np] FP64 positions (split into hi/lo per CTA / per tile)
+    const float *dc32, *tw32;          // [n_tiles*4096], [R][n_tiles*4096]
+    double *Grow, *P;
+    const unsigned char *tile_clean;
+    int n_kg;
+};
+
+__global__ void __launch_bounds__(128, 4)
+backward_tile32_kernel(DevModel dm, TileDev td, BackwardTile32Args ba)
+{
+    extern __shared__ __align__(16) double smem[];        // [STAGES][2][1024] floats: dc, w
+    float *sf = reinterpret_cast<float *>(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kg = blockIdx.x % ba.n_kg;
+    const int I = (blockIdx.x / ba.n_kg) % td.n_rb;
+    const int r = blockIdx.x / (ba.n_kg * td.n_rb);
+    const int k = kg * 4 + warp;
+    const bool k_ok = k < dm.S;
+    const long long rk = (long long)r * dm.S + (k_ok ? k : dm.S - 1);
+    const int Np = dm.Np;
+    const double *xk = ba.xs + rk * 3LL * Np;
+    const int row0 = 128 * I + lane;
+    float xh[4][3], xl[4][3], acc[4][3];
+    double acc64[4][3];
+    auto split = [](double x, float &hi, float &lo) { hi = __double2float_rn(x); lo = __double2float_rn(x - (double)hi); };
+#pragma unroll
+    for (int rb = 0; rb < 4; rb++) {
+        const int b0 = row0 + 32 * rb;
+        const int b = b0 < dm.N ? b0 : 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            split(xk[c * Np + b], xh[rb][c], xl[rb][c]);
+            acc[rb][c] = 0.0f; acc64[rb][c] = 0.0;
+        }
+    }
+    const float alpha = (float)dm.alpha;
+    const float *twr = ba.tw32 + (long long)r * td.slots;
+    double *Pk = ba.P + (rk * td.n_rb + I) * (long long)dm.N * 3;
+    const int t0 = td.rb_begin[I], n_tiles = td.rb_begin[I + 1] - t0;
+    const int n_chunks = n_tiles * 4;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(sf + EHIC_BT_STAGES * 2048);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < EHIC_BT_STAGES; q++) mbar_init(&full[q], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int c) {
+        if (c < n_chunks && threadIdx.x == 0) {
+            const int st = c % EHIC_BT_STAGES;
+            const long long base = (long long)(t0 + (c >> 2)) * 4096 + (c & 3) * 1024;
+            float *d0 = sf + st * 2048;
+            mbar_expect_tx(&full[st], 2 * 1024 * (unsigned)sizeof(float));
+            bulk_g2s(d0, ba.dc32 + base, 1024 * (unsigned)sizeof(float), &full[st]);
+            bulk_g2s(d0 + 1024, twr + base, 1024 * (unsigned)sizeof(float), &full[st]);
+        }
+    };
+#pragma unroll
+    for (int c = 0; c < EHIC_BT_STAGES - 1; c++) issue(c);
+
+    float ch[3] = {0.f, 0.f, 0.f}, cl[3] = {0.f, 0.f, 0.f};
+    unsigned m[4] = {0u, 0u, 0u, 0u};
+    int col0 = 0;
+    bool clean = false;
+    for (int c = 0; c < n_chunks; c++) {
+        mbar_wait(&full[c % EHIC_BT_STAGES], (unsigned)((c / EHIC_BT_STAGES) & 1));
+        __syncthreads();
+        issue(c + EHIC_BT_STAGES - 1);
+        const int qg = c & 3;
+        if (qg == 0) {
+            const int t = t0 + (c >> 2);
+            col0 = 32 * td.tile_B[t];
+            const int oc = min(col0 + lane, dm.N - 1);
+#pragma unroll
+            for (int u = 0; u < 3; u++) split(xk[u * Np + oc], ch[u], cl[u]);
+            clean = ba.tile_clean[t] != 0;
+#pragma unroll
+            for (int rb = 0; rb < 4; rb++) m[rb] = clean ? 0xffffffffu : td.mask[((long long)t * 4 + rb) * 32 + lane];
+        }
+        const float *sd = sf + (c % EHIC_BT_STAGES) * 2048 + lane;
+        float rx[8], ry[8], rz[8];
+#pragma unroll
+        for (int qq = 0; qq < 8; qq++) {
+            const int q = qg * 8 + qq;
+            const float oxh = __shfl_sync(0xffffffffu, ch[0], q), oyh = __shfl_sync(0xffffffffu, ch[1], q),
+                        ozh = __shfl_sync(0xffffffffu, ch[2], q);
+            const float oxl = __shfl_sync(0xffffffffu, cl[0], q), oyl = __shfl_sync(0xffffffffu, cl[1], q),
+                        ozl = __shfl_sync(0xffffffffu, cl[2], q);
+            float fx = 0.f, fy = 0.f, fz = 0.f;
+#pragma unroll
+            for (int rb = 0; rb < 4; rb++) {
+                const float dc = sd[(qq * 4 + rb) * 32], w = sd[1024 + (qq * 4 + rb) * 32];
+                const float dx = (oxh - xh[rb][0]) + (oxl - xl[rb][0]);
+                const float dy = (oyh - xh[rb][1]) + (oyl - xl[rb][1]);
+                const float dz = (ozh - xh[rb][2]) + (ozl - xl[rb][2]);
+                const float s2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                const float rd = rsqrt_f32(s2);
+                const float tt = alpha * (dc - s2 * rd);
+                const float rq = rsqrt_f32_raw(fmaf(tt, tt, 1.0f));
+                float f = w * ((rq * rq) * (rq * rd));
+                f = ((m[rb] >> q) & 1u) ? f : 0.0f;
+                acc[rb][0] = fmaf(f, dx, acc[rb][0]); acc[rb][1] = fmaf(f, dy, acc[rb][1]); acc[rb][2] = fmaf(f, dz, acc[rb][2]);
+                fx = fmaf(-f, dx, fx); fy = fmaf(-f, dy, fy); fz = fmaf(-f, dz, fz);
+            }
+            rx[qq] = fx; ry[qq] = fy; rz[qq] = fz;
+        }
+        reduce8_t(rx, lane); reduce8_t(ry, lane); reduce8_t(rz, lane);
+        if ((lane & 3) == 0 && k_ok) {
+            const int sub = ((lane >> 2) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 4) & 1);
+            const int col = col0 + qg * 8 + sub;
+            if (col < dm.N) { double *o = Pk + (long long)col * 3; o[0] = (double)rx[0]; o[1] = (double)ry[0]; o[2] = (double)rz[0]; }
+        }
+        if (qg == 3) {                                   // tile done: flush the FP32 row accumulators
+#pragma unroll
+            for (int rb = 0; rb < 4; rb++)
+#pragma unroll
+                for (int u = 0; u < 3; u++) { acc64[rb][u] += (double)acc[rb][u]; acc[rb][u] = 0.0f; }
+        }
+    }
+    if (k_ok) {
+#pragma unroll
+        for (int rb = 0; rb < 4; rb++) {
+            const int b = row0 + 32 * rb;
+            if (b < dm.N) { double *o = ba.Grow + (rk * dm.N + b) * 3; o[0] = acc64[rb][0]; o[1] = acc64[rb][1]; o[2] = acc64[rb][2]; }
+        }
+    }
+}
+
 // Combine + epilogue of the tile path: thread <-> (replica, structure, bead).
 // g = (row sum + sum over row blocks of the reaction partials, ascending) + gprior,
 // then the same leapfrog epilogue as gather_kernel.
 __global__ void __launch_bounds__(256)
 combine_kernel(DevModel dm, TileDev td, GatherArgs ga, const double *__restrict__ Grow, const double *__restrict__ P,
-               int contact, int KT, int nkt)
+               int contact, int KT, int nkt, int f32)
 {
     const int k = blockIdx.y, r = blockIdx.z;
     const int b = blockIdx.x * 256 + threadIdx.x;
@@ -1647,7 +1967,8 @@ combine_kernel(DevModel dm, TileDev td, GatherArgs ga, const double *__restrict_
                 double *xn = ga.xs_next + rk * 3LL * Np;
                 xn[b] = n0; xn[Np + b] = n1; xn[2 * Np + b] = n2;
                 double *un = ga.xt_next + ((((long long)r * nkt + k / KT) * Np + b) * KT + (k % KT)) * 3;
-                un[0] = n0; un[1] = n1; un[2] = n2;
+                if (f32) { un[0] = split_hilo(n0); un[1] = split_hilo(n1); un[2] = split_hilo(n2); }
+                else { un[0] = n0; un[1] = n1; un[2] = n2; }
             }
         }
     }

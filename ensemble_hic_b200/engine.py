@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (TERM_ALL, TERM_BACKBONE, TERM_LIKELIHOOD, TERM_NONBONDED, TERM_SPHERE,  # noqa: F401
-                   FLAG_EXACT, N_ENERGIES)
+                   FLAG_EXACT, FLAG_FP32, N_ENERGIES)
 
 
 def _f64(a):
@@ -31,7 +31,7 @@ def _ptr(a):
 class Model(object):
     def __init__(self, n_structures, bead_radii, data_points=None, contact_distances=None,
                  alpha=1.0, k_nb=0.0, k_bb=0.0, bb_lower=None, bb_upper=None, mol_ranges=None,
-                 sphere=None, max_replicas=1, exact=False, device=0):
+                 sphere=None, max_replicas=1, exact=False, device=0, fp32=False):
         L = _lib.lib()
         radii = _f64(bead_radii).ravel()
         N = len(radii)
@@ -70,7 +70,7 @@ class Model(object):
             d.sphere_active, d.sphere_radius, d.sphere_k = 1, float(R), float(k)
             d.sphere_center[0], d.sphere_center[1], d.sphere_center[2] = float(c[0]), float(c[1]), float(c[2])
         d.max_replicas = int(max_replicas)
-        d.flags = FLAG_EXACT if exact else 0
+        d.flags = (FLAG_EXACT if exact else 0) | (FLAG_FP32 if fp32 else 0)
         h = C.c_void_p()
         _lib.check(L.ehic_model_create(C.byref(d), int(device), C.byref(h)))
         self._L, self._h = L, h
@@ -78,6 +78,7 @@ class Model(object):
         self.max_replicas = int(max_replicas)
         self.device = int(device)
         self.exact = bool(exact)
+        self.fp32 = bool(fp32)
         self.sphere_active = sphere is not None
 
     def close(self):

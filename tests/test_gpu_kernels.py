@@ -279,6 +279,82 @@ def test_tile_path_trajectory(co, monkeypatch):
         assert abs(H[r, 3] - 0.5 * np.sum(p1 ** 2)) <= 1e-9 * H[r, 3]
 
 
+# ---- optional FP32 mode (north star: 1e-5 relative on log-posterior and gradient) ----------------------
+
+FP32_TOL = 1e-5
+
+
+@pytest.mark.parametrize("S,N,density,shift", [(5, 257, 1.0, 0.0), (7, 300, 0.9, 0.0), (3, 100, 1.0, 300.0), (12, 130, 0.6, 0.0),
+                                               (4, 64, 1.0, -1000.0)])
+def test_fp32_mode_within_1e5_of_oracle(co, monkeypatch, S, N, density, shift):
+    """FP32 pair arithmetic in the tile kernels; `shift` moves the whole ensemble away from the origin
+    (the (hi, lo) coordinate split keeps differences accurate)."""
+    from oracle.oracle import OraclePosterior
+    monkeypatch.setenv("EHIC_TILE_MIN_FILL", "0.2")            # small dense lists fill few of their 128 x 32 tiles
+    pb = make_problem(seed=S * 1000 + N, S=S, N=N, density=density, uniform_radii=False, step=0.7)
+    ul = pb["radii"][:-1] + pb["radii"][1:]
+    op = OraclePosterior(S, pb["data"], pb["cds"], pb["alpha"], pb["radii"], 50.0, 500.0,
+                         [np.zeros(N - 1)], [ul], [0, N], nonbonded="n2")
+    R = 3
+    rng = np.random.default_rng(1)
+    X = np.stack([pb["X"] + rng.normal(scale=0.03, size=pb["X"].shape) for _ in range(R)]) + shift
+    norm = rng.uniform(1, 5, R); lam = np.array([0.2, 1.0, 0.6]); bet = np.array([1.0, 0.3, 0.0])
+    m = _model(pb, False, max_replicas=R, fp32=True)
+    assert m.info()["path"] == "tiles" and m.info()["flags"] & 2
+    out = m.evaluate(X, norm, lam, bet, energies=True, md=True)
+    for r in range(R):
+        ref_md = op.mock_data(X[r], norm[r])
+        np.testing.assert_allclose(out["md"][r], ref_md, rtol=2e-5)                # element-wise, far pairs included
+        assert relerr(out["md"][r], ref_md) < FP32_TOL
+        assert relerr(out["grad"][r], op.gradient(X[r], norm[r], lam[r], bet[r])) < FP32_TOL
+        E = op.energies(X[r], norm[r])
+        assert abs(out["energies"][r, 0] - E[0]) <= FP32_TOL * abs(E[0])             # -log L
+        np.testing.assert_allclose(out["energies"][r, 1:], E[1:], rtol=1e-11)        # priors stay FP64
+    glik = m.evaluate(X[0], norm[0], terms=1)["grad"][0]
+    assert relerr(glik, co.calculate_gradient(X[0], pb["alpha"], norm[0], pb["cds"], pb["data"])) < FP32_TOL
+    # and it is a different arithmetic, not the FP64 path under another name
+    m64 = _model(pb, False, max_replicas=R)
+    g64 = m64.evaluate(X, norm, lam, bet)["grad"]
+    assert 1e-9 < relerr(out["grad"], g64) < FP32_TOL
+
+
+def test_fp32_mode_needs_a_dense_list_and_excludes_exact():
+    from ensemble_hic_b200.engine import Model
+    sparse = make_problem(seed=3, S=2, N=256, density=0.1)
+    with pytest.raises(Exception, match="dense contact list"):
+        _model(sparse, False, fp32=True)
+    dense = make_problem(seed=3, S=2, N=128, density=1.0)
+    with pytest.raises(Exception, match="exclude"):
+        _model(dense, True, fp32=True)
+
+
+def test_fp32_mode_trajectory(monkeypatch):
+    """a leapfrog trajectory in FP32 mode stays within 1e-5 of the FP64 trajectory over a few steps"""
+    import torch
+    monkeypatch.setenv("EHIC_TRAJ", "multi")
+    monkeypatch.setenv("EHIC_TILE_MIN_FILL", "0.2")
+    pb = make_problem(seed=77, S=3, N=140, step=0.8)
+    R, L = 2, 6
+    rng = np.random.default_rng(0)
+    X = np.stack([pb["X"], pb["X"] + rng.normal(scale=0.05, size=pb["X"].shape)]).reshape(R, -1)
+    P = rng.normal(size=X.shape)
+    norm = np.array([2.5, 3.5]); lam = np.array([0.3, 1.0]); bet = np.array([0.5, 1.0]); eps = np.array([5e-4, 1e-3])
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    res = {}
+    for fp32 in (False, True):
+        m = _model(pb, False, max_replicas=R, fp32=fp32)
+        x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
+        m.hmc_trajectory_device(R, L, x_t, p_t, t(norm), t(lam), t(bet), t(eps), H_t)
+        torch.cuda.synchronize()
+        res[fp32] = (x_t.cpu().numpy(), p_t.cpu().numpy(), H_t.cpu().numpy())
+        m.close()
+    assert relerr(res[True][0], res[False][0]) < 1e-8          # positions move by eps^2 * gradient error
+    assert relerr(res[True][1], res[False][1]) < FP32_TOL
+    np.testing.assert_allclose(res[True][2], res[False][2], rtol=FP32_TOL)
+    assert not np.array_equal(res[True][1], res[False][1])
+
+
 # ---- lane path (sparse lists, fast mode: lane <-> structure) -------------------------------------------
 
 @pytest.mark.parametrize("S,N,density,min_sep", [(30, 64, 0.3, 1), (33, 50, 0.5, 1), (64, 40, 1.0, 1), (20, 100, 0.1, 2),

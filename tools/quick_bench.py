@@ -31,7 +31,7 @@ def main():
     counts = rng.poisson(2.0, size=M)
     data = np.stack([i, j, counts], 1).astype(np.int64)
     t0 = time.time()
-    m = Model(S, radii, data, cds, alpha=10.0, k_nb=500.0, k_bb=500.0, max_replicas=R)
+    m = Model(S, radii, data, cds, alpha=10.0, k_nb=500.0, k_bb=500.0, max_replicas=R, fp32=bool(os.environ.get("QB_FP32")))
     print("model create %.2fs" % (time.time() - t0), m.info(), flush=True)
     for fp64 in (True, False):
         print("fma peak fp64=%s: %.2f TFLOP/s (%.3f ms/launch)" % ((fp64,) + fma_peak(fp64, 10)), flush=True)
