@@ -327,6 +327,28 @@ def run_b200(args):
                   "hmc_acceptance": float(np.mean(rex.n_acc_T / np.maximum(rex.n_hmc_T, 1))),
                   "replica_trajectories_per_s": n_total * (args.sweeps - 1) / float(dts.item())}
 
+    # ---- optional FP32 mode (north star: 1e-5 relative), same step, reported beside the FP64 headline ------
+    fp32_mode = None
+    if rank == 0 and world == 1 and model.info()["path"] == "tiles":
+        m32 = Model(S, pb["radii"], data, pb["cds"], alpha=ALPHA, k_nb=K_NB, k_bb=K_BB, max_replicas=R, device=local, fp32=True)
+        g32 = torch.empty_like(x)
+        step()
+        for _ in range(3):
+            m32.evaluate_device(R, x, norm, lam, bet, grad=g32)
+        torch.cuda.synchronize()
+        n32 = max(3, min(args.steps, 20))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(n32):
+            m32.evaluate_device(R, x, norm, lam, bet, grad=g32)
+        a1.record()
+        torch.cuda.synchronize()
+        ms32 = a0.elapsed_time(a1) / n32
+        fp32_mode = {"value": R / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32, "dtype": "f32 pair arithmetic, f64 I/O",
+                     "grad_max_rel_dev_from_f64": float((g32 - g).abs().max() / g.abs().max())}
+        m32.close()
+        del g32
+
     # ---- per-kernel durations (CUDA events on the launching stream, same call sequence) ------
     kern = None
     if rank == 0:
@@ -375,7 +397,8 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_x + 3 * R * 8,
                         "d2h_bytes_per_step": bytes_x,
                         "api": "ehic_evaluate_host (C ABI) with pinned host buffers, batched over the GPU's replicas"},
-                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "re_sweeps": sweeps}
+                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "re_sweeps": sweeps,
+                "fp32_mode": fp32_mode}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -18,6 +18,12 @@ _CACHE = OrderedDict()
 _MAX = int(os.environ.get("EHIC_MODEL_CACHE", "8"))
 
 
+def default_fp32():
+    """EHIC_FP32=1 selects the optional FP32 pair arithmetic (dense contact lists only) for posteriors built
+    by make_posterior."""
+    return os.environ.get("EHIC_FP32", "0") not in ("0", "", "false", "False")
+
+
 def default_exact():
     """EHIC_EXACT=1 selects the bit-exact arithmetic mode for models built implicitly."""
     return os.environ.get("EHIC_EXACT", "0") not in ("0", "", "false", "False")

@@ -88,8 +88,12 @@ struct ehic_model {
     std::vector<Timed> timed;
     // staging for the host entry points
     double *st_x = nullptr, *st_g = nullptr, *st_md = nullptr, *st_small = nullptr;
-    cudaStream_t st_stream = nullptr, st_in = nullptr, st_out = nullptr;
-    cudaEvent_t ev_in[4] = {nullptr, nullptr, nullptr, nullptr}, ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t st_stream = nullptr, st_stream2 = nullptr, st_in = nullptr, st_out = nullptr;
+    static constexpr int kMaxChunks = 8;
+    cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
+    // per-replica strides (elements) of the workspace arrays, for evaluating a chunk in replica slots [s, s+n)
+    struct WsStrides { size_t xs = 0, xt = 0, wbuf = 0, tw = 0, gprior = 0, bbox = 0, partC = 0, partA = 0, partP = 0,
+                       partK = 0, Grow = 0, Pbuf = 0, cell = 0; } wss;
 };
 
 static void drop_graphs(ehic_model *m)
@@ -368,6 +372,13 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     DA(m->partP, Rm * (size_t)S * m->nPx * 3);
     DA(m->partK, Rm * std::max((size_t)L.n_slices * m->nktg * m->gw, (size_t)m->n_quads * EHIC_LANE_WARPS * m->nkt));
     DA(m->energies, Rm * 4); DA(m->kinetic, Rm);
+    {
+        auto &w = m->wss;
+        w.xs = (size_t)S * 3 * dm.Np; w.xt = (size_t)m->nkt * dm.Np * m->kt * 3; w.wbuf = (size_t)dm.wstride;
+        w.gprior = (size_t)S * N * 3; w.bbox = (size_t)S * L.n_slices * 6; w.partC = (size_t)S; w.cell = (size_t)S * N;
+        w.partA = (size_t)std::max(m->nA, 1); w.partP = (size_t)S * m->nPx * 3;
+        w.partK = std::max((size_t)L.n_slices * m->nktg * m->gw, (size_t)m->n_quads * EHIC_LANE_WARPS * m->nkt);
+    }
     if (m->use_tiles) {
         m->nA_tile = m->td.n_tiles;                                   // one forward CTA (partial) per tile
         m->nKc = (N + 255) / 256;
@@ -377,6 +388,9 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         double *pa2 = nullptr, *pk2 = nullptr;                         // partials sized for the tile kernels
         DA(pa2, Rm * (size_t)std::max(std::max(m->nA_tile, m->nA), 1)); m->partA = pa2;
         DA(pk2, Rm * (size_t)std::max<size_t>((size_t)S * m->nKc, (size_t)L.n_slices * m->nktg * m->gw)); m->partK = pk2;
+        m->wss.partA = (size_t)std::max(std::max(m->nA_tile, m->nA), 1);
+        m->wss.partK = std::max<size_t>((size_t)S * m->nKc, (size_t)L.n_slices * m->nktg * m->gw);
+        m->wss.tw = (size_t)m->td.slots; m->wss.Grow = (size_t)S * N * 3; m->wss.Pbuf = (size_t)S * m->td.n_rb * N * 3;
         if (cudaMemset(m->tw, 0, Rm * (size_t)m->td.slots * sizeof(double)) != cudaSuccess) {
             ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed");
         }
@@ -416,9 +430,10 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed");
     }
     bool ok = cudaStreamCreateWithFlags(&m->st_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&m->st_stream2, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&m->st_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&m->st_out, cudaStreamNonBlocking) == cudaSuccess;
-    for (int q = 0; ok && q < 4; q++)
+    for (int q = 0; ok && q < ehic_model::kMaxChunks; q++)
         ok = cudaEventCreateWithFlags(&m->ev_in[q], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&m->ev_done[q], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "stream / event creation failed"); }
@@ -434,9 +449,10 @@ int ehic_model_destroy(ehic_model_t *m)
     for (void *p : m->owned) cudaFree(p);
     cudaFree(m->st_x); cudaFree(m->st_g); cudaFree(m->st_md); cudaFree(m->st_small);
     if (m->st_stream) cudaStreamDestroy(m->st_stream);
+    if (m->st_stream2) cudaStreamDestroy(m->st_stream2);
     if (m->st_in) cudaStreamDestroy(m->st_in);
     if (m->st_out) cudaStreamDestroy(m->st_out);
-    for (int q = 0; q < 4; q++) { if (m->ev_in[q]) cudaEventDestroy(m->ev_in[q]); if (m->ev_done[q]) cudaEventDestroy(m->ev_done[q]); }
+    for (int q = 0; q < ehic_model::kMaxChunks; q++) { if (m->ev_in[q]) cudaEventDestroy(m->ev_in[q]); if (m->ev_done[q]) cudaEventDestroy(m->ev_done[q]); }
     delete m;
     return EHIC_OK;
 }
@@ -692,6 +708,34 @@ static int launch_finalize(ehic_model *m, int R, bool haveA, bool haveP, bool ha
     CU(cudaGetLastError());
     return EHIC_OK;
 }
+
+// RAII: rebases the per-replica workspace pointers of the model to replica slot `s` while a chunk is being
+// enqueued (kernel arguments are captured at launch), so that two chunks can be in flight at once.
+struct SlotShift {
+    ehic_model *m;
+    double *xs0, *xt0, *wbuf, *tw, *gprior, *bbox, *partC, *partA, *partP, *partK, *Grow, *Pbuf;
+    float *tw32;
+    int *cell;
+    SlotShift(ehic_model *m_, int s) : m(m_)
+    {
+        xs0 = m->xs[0]; xt0 = m->xt[0]; wbuf = m->wbuf; tw = m->tw; gprior = m->gprior; bbox = m->bbox; partC = m->partC;
+        partA = m->partA; partP = m->partP; partK = m->partK; Grow = m->Grow; Pbuf = m->Pbuf; tw32 = m->tw32; cell = m->cell_list;
+        const auto &w = m->wss;
+        const size_t z = (size_t)s;
+        m->xs[0] += z * w.xs; m->xt[0] += z * w.xt; m->wbuf += z * w.wbuf; m->gprior += z * w.gprior; m->bbox += z * w.bbox;
+        m->partC += z * w.partC; m->partA += z * w.partA; m->partP += z * w.partP; m->partK += z * w.partK;
+        if (m->tw) m->tw += z * w.tw;
+        if (m->tw32) m->tw32 += z * w.tw;
+        if (m->Grow) m->Grow += z * w.Grow;
+        if (m->Pbuf) m->Pbuf += z * w.Pbuf;
+        if (m->cell_list) m->cell_list += z * w.cell;
+    }
+    ~SlotShift()
+    {
+        m->xs[0] = xs0; m->xt[0] = xt0; m->wbuf = wbuf; m->tw = tw; m->gprior = gprior; m->bbox = bbox; m->partC = partC;
+        m->partA = partA; m->partP = partP; m->partK = partK; m->Grow = Grow; m->Pbuf = Pbuf; m->tw32 = tw32; m->cell_list = cell;
+    }
+};
 
 extern "C" {
 
@@ -970,11 +1014,12 @@ int ehic_evaluate_host(ehic_model_t *m, int R, int terms, const double *h_x, con
     if (!h_x) return fail(EHIC_ERR_INVALID, "null coordinates");
     rc = ensure_staging(m);
     if (rc) return rc;
-    // Software pipeline over chunks of replicas on three streams: the H2D copy of chunk c+1 and the
-    // D2H copy of chunk c-1 overlap the kernels of chunk c (kernels run one chunk at a time, so the
-    // model's workspace is reused).  Over PCIe the two 38 MB copies of config D would otherwise add
-    // ~20 % to the step.
-    cudaStream_t st = m->st_stream, s_in = m->st_in, s_out = m->st_out;
+    // Software pipeline over chunks of replicas: all input copies are queued on one stream, the kernels of
+    // consecutive chunks alternate between two compute streams (each chunk works in its own replica slots of
+    // the workspace, so chunk c+1 fills the partial last wave of chunk c), and output copies follow on a
+    // third stream.  Exposed: the first chunk's H2D and the last chunk's D2H.  Over PCIe the two 38 MB
+    // copies of config D would otherwise add ~40 % to the step.
+    cudaStream_t s_in = m->st_in, s_out = m->st_out;
     const size_t per = (size_t)m->dm.S * (size_t)m->dm.N * 3;
     const size_t M = (size_t)m->dm.M;
     double *d_norm = m->st_small, *d_lam = m->st_small + m->max_replicas, *d_bet = m->st_small + 2 * (size_t)m->max_replicas;
@@ -982,7 +1027,9 @@ int ehic_evaluate_host(ehic_model_t *m, int R, int terms, const double *h_x, con
     if (h_norm) CU(cudaMemcpyAsync(d_norm, h_norm, sizeof(double) * R, cudaMemcpyHostToDevice, s_in));
     if (h_lammda) CU(cudaMemcpyAsync(d_lam, h_lammda, sizeof(double) * R, cudaMemcpyHostToDevice, s_in));
     if (h_beta) CU(cudaMemcpyAsync(d_bet, h_beta, sizeof(double) * R, cudaMemcpyHostToDevice, s_in));
-    const int n_chunks = std::min(R, 4);
+    static const int chunk_cap = []() { const char *e = getenv("EHIC_HOST_CHUNKS"); int v = e ? atoi(e) : 0;
+                                        return (v >= 1 && v <= ehic_model::kMaxChunks) ? v : 4; }();      // 4 measured best at config D (8 replicas)
+    const int n_chunks = std::min(R, chunk_cap);
     for (int c = 0; c < n_chunks; c++) {
         const int r0 = (int)((long long)R * c / n_chunks), r1 = (int)((long long)R * (c + 1) / n_chunks);
         CU(cudaMemcpyAsync(m->st_x + r0 * per, h_x + r0 * per, sizeof(double) * per * (r1 - r0), cudaMemcpyHostToDevice, s_in));
@@ -990,11 +1037,15 @@ int ehic_evaluate_host(ehic_model_t *m, int R, int terms, const double *h_x, con
     }
     for (int c = 0; c < n_chunks; c++) {
         const int r0 = (int)((long long)R * c / n_chunks), r1 = (int)((long long)R * (c + 1) / n_chunks);
+        cudaStream_t st = (c & 1) ? m->st_stream2 : m->st_stream;
         CU(cudaStreamWaitEvent(st, m->ev_in[c], 0));
-        rc = ehic_evaluate(m, r1 - r0, terms, m->st_x + r0 * per, h_norm ? d_norm + r0 : nullptr,
-                           h_lammda ? d_lam + r0 : nullptr, h_beta ? d_bet + r0 : nullptr,
-                           h_grad ? m->st_g + r0 * per : nullptr, h_energies ? d_E + 4 * (size_t)r0 : nullptr,
-                           h_md ? m->st_md + r0 * M : nullptr, st);
+        {
+            SlotShift shift(m, r0);
+            rc = ehic_evaluate(m, r1 - r0, terms, m->st_x + r0 * per, h_norm ? d_norm + r0 : nullptr,
+                               h_lammda ? d_lam + r0 : nullptr, h_beta ? d_bet + r0 : nullptr,
+                               h_grad ? m->st_g + r0 * per : nullptr, h_energies ? d_E + 4 * (size_t)r0 : nullptr,
+                               h_md ? m->st_md + r0 * M : nullptr, st);
+        }
         if (rc) { cudaDeviceSynchronize(); return rc; }
         CU(cudaEventRecord(m->ev_done[c], st));
         CU(cudaStreamWaitEvent(s_out, m->ev_done[c], 0));
@@ -1003,7 +1054,8 @@ int ehic_evaluate_host(ehic_model_t *m, int R, int terms, const double *h_x, con
     }
     if (h_energies) CU(cudaMemcpyAsync(h_energies, d_E, sizeof(double) * 4 * R, cudaMemcpyDeviceToHost, s_out));
     CU(cudaStreamSynchronize(s_out));
-    CU(cudaStreamSynchronize(st));
+    CU(cudaStreamSynchronize(m->st_stream));
+    CU(cudaStreamSynchronize(m->st_stream2));
     return EHIC_OK;
 }
 

@@ -42,11 +42,12 @@ def update_ensemble_setting(settings):
     return settings
 
 
-def make_posterior(settings, max_replicas=1, exact=None, device=None):
+def make_posterior(settings, max_replicas=1, exact=None, device=None, fp32=None):
     """``p = make_posterior(parse_config_file('config.cfg'))`` (reference: setup_functions.py:64-98).
 
     Extra keyword arguments size the resident GPU model: ``max_replicas`` tempered copies can be
-    evaluated per call by the batched drivers; ``exact`` selects the bit-exact arithmetic mode."""
+    evaluated per call by the batched drivers; ``exact`` selects the bit-exact arithmetic mode, ``fp32``
+    the optional FP32 pair arithmetic (1e-5 relative; dense contact lists only)."""
     from . import _models
     from .engine import Model
     from .posteriors import GPUPosterior
@@ -77,6 +78,7 @@ def make_posterior(settings, max_replicas=1, exact=None, device=None):
                    k_bb=bbp["k_bb"].value, bb_lower=ll, bb_upper=ul, mol_ranges=bbp._mol_ranges,
                    sphere=sphere, max_replicas=max_replicas,
                    exact=_models.default_exact() if exact is None else exact,
+                   fp32=_models.default_fp32() if fp32 is None else fp32,
                    device=_models.default_device() if device is None else device)
     fwm.attach_engine(engine)
     for p in priors.values():
