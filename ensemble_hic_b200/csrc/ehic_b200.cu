@@ -1100,6 +1100,18 @@ int ehic_layout_debug(int32_t n_beads, int64_t n_data, const int64_t *data_point
         if (L.ent_j[L.slot_a[s]] != L.pj[s] || L.ent_j[L.slot_b[s]] != L.pi[s])
             return fail(EHIC_ERR_INVALID, "internal: row view inconsistent");
     }
+    if (!exact_order) {     // same self-check for the lane view (CSR) of the sparse path
+        LaneLayout C;
+        err = build_lanes(L, C);
+        if (!err.empty()) return fail(EHIC_ERR_INVALID, err);
+        if (C.row_off[n_beads] != 2 * n_data) return fail(EHIC_ERR_INVALID, "internal: lane view has the wrong size");
+        for (int64_t s = 0; s < n_data; s++) {
+            const int64_t a = C.slot_a[s], b = C.slot_b[s];
+            const bool ok = a >= C.row_off[L.pi[s]] && a < C.row_off[L.pi[s] + 1] && b >= C.row_off[L.pj[s]] &&
+                            b < C.row_off[L.pj[s] + 1] && C.ent_j[a] == L.pj[s] && C.ent_j[b] == L.pi[s];
+            if (!ok) return fail(EHIC_ERR_INVALID, "internal: lane view inconsistent");
+        }
+    }
     return EHIC_OK;
 }
 

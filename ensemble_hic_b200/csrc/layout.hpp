@@ -258,11 +258,13 @@ inline std::string build_lanes(const ContactLayout &L, LaneLayout &C)
     C.ent_j.resize((size_t)2 * M); C.ent_dc.resize((size_t)2 * M);
     C.slot_a.resize(M); C.slot_b.resize(M);
     std::vector<int64_t> fill(C.row_off.begin(), C.row_off.end() - 1);
+    const bool have_dc = !L.pdc.empty();
     for (int64_t s = 0; s < M; s++) {
         const int32_t i = L.pi[s], j = L.pj[s];
+        const double dc = have_dc ? L.pdc[s] : 0.0;
         int64_t a = fill[i]++, b = fill[j]++;
-        C.ent_j[a] = j; C.ent_dc[a] = L.pdc[s]; C.slot_a[s] = (int32_t)a;
-        C.ent_j[b] = i; C.ent_dc[b] = L.pdc[s]; C.slot_b[s] = (int32_t)b;
+        C.ent_j[a] = j; C.ent_dc[a] = dc; C.slot_a[s] = (int32_t)a;
+        C.ent_j[b] = i; C.ent_dc[b] = dc; C.slot_b[s] = (int32_t)b;
     }
     return "";
 }
