@@ -390,6 +390,22 @@ def test_lane_path_matches_oracle(co, monkeypatch, S, N, density, min_sep):
     assert relerr(out["grad"], out2["grad"]) < 1e-13 and relerr(out["md"], out2["md"]) < 1e-13
 
 
+def test_lane_path_reversed_and_duplicate_pairs(co, monkeypatch):
+    """data points given as (j, i) with j > i, and the same bead pair listed twice (allowed by the reference:
+    every row of data_points is its own Poisson term)"""
+    monkeypatch.setenv("EHIC_PATH", "lanes")
+    pb = make_problem(seed=5, S=32, N=45, density=0.4)
+    data, cds = pb["data"].copy(), pb["cds"].copy()
+    data[::3, :2] = data[::3, 1::-1]                            # every third pair reversed
+    data = np.concatenate([data, data[:40]]); cds = np.concatenate([cds, cds[:40] * 1.1])     # 40 duplicates, other dc
+    pb2 = dict(pb, data=np.ascontiguousarray(data), cds=np.ascontiguousarray(cds))
+    m = _model(pb2, False)
+    assert m.info()["path"] == "lanes"
+    out = m.evaluate(pb["X"], pb["norm"], terms=1, md=True)
+    assert relerr(out["md"][0], co.ensemble_contacts_evaluate(pb["X"], pb["norm"], cds, pb["alpha"], data)) < FAST_TOL
+    assert relerr(out["grad"][0], co.calculate_gradient(pb["X"], pb["alpha"], pb["norm"], cds, data)) < FAST_TOL
+
+
 def test_lane_path_is_chosen_for_sparse_lists_with_enough_structures(monkeypatch):
     monkeypatch.delenv("EHIC_PATH", raising=False)
     assert _model(make_problem(seed=3, S=30, N=256, density=0.1), False).info()["path"] == "lanes"
