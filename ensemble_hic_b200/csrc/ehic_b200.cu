@@ -69,6 +69,8 @@ struct ehic_model {
     double *wbuf = nullptr, *gprior = nullptr, *bbox = nullptr, *partC = nullptr;
     int *cell_list = nullptr;
     bool use_cells = false;         // fast mode: nonbonded term through the per-structure cell grid
+    bool use_verlet = false;        // HMC trajectories: nonbonded term from Verlet lists reused across leapfrog steps
+    VerletDev vl{};
     double *partA = nullptr, *partP = nullptr, *partK = nullptr;
     double *energies = nullptr, *kinetic = nullptr;
     int nA = 0;                     // forward blocks per replica
@@ -368,6 +370,24 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
             m->owned.push_back(cl); m->cell_list = cl;
         }
     }
+    {   // Verlet lists (trajectories only): fast mode, all-pairs regime, bounded memory
+        const char *ve = getenv("EHIC_VERLET");
+        const size_t idx_bytes = sizeof(unsigned short) * Rm * S * (size_t)EHIC_VL_CAP * dm.Np;
+        m->use_verlet = !exact && !m->use_cells && N >= 32 && desc->nonbonded_k != 0.0 && !(ve && !strcmp(ve, "0")) &&
+                        idx_bytes <= ((size_t)8 << 30);
+        if (m->use_verlet) {
+            const char *sk = getenv("EHIC_VERLET_SKIN");
+            m->vl.skin = (sk ? atof(sk) : 0.5) * m->r_max;
+            if (!(m->vl.skin > 0.0)) m->vl.skin = 0.5 * m->r_max;
+            int *ip = nullptr;
+            const size_t n_int = Rm * S * (size_t)(2 + dm.Np + 32) / 32 * 32 + idx_bytes / sizeof(int);
+            if (cudaMalloc(&ip, sizeof(int) * n_int) != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_NOMEM, "cudaMalloc failed"); }
+            m->owned.push_back(ip);
+            if (cudaMemset(ip, 0, sizeof(int) * Rm * S * (size_t)(2 + dm.Np)) != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed"); }
+            m->vl.state = ip; m->vl.stale = ip + Rm * S; m->vl.cnt = ip + 2 * Rm * S; m->vl.idx = reinterpret_cast<unsigned short *>(ip + Rm * S * (size_t)(2 + dm.Np + 32) / 32 * 32);     // 128-byte aligned
+            DA(m->vl.xref, xs_n);
+        }
+    }
     DA(m->partA, Rm * (size_t)std::max(m->nA, 1));
     DA(m->partP, Rm * (size_t)S * m->nPx * 3);
     DA(m->partK, Rm * std::max((size_t)L.n_slices * m->nktg * m->gw, (size_t)m->n_quads * EHIC_LANE_WARPS * m->nkt));
@@ -591,8 +611,9 @@ static int launch_forward(ehic_model *m, int R, const double *xs, const double *
 }
 
 static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const double *d_beta,
-                        bool want_grad, bool want_energy, cudaStream_t st)
+                        bool want_grad, bool want_energy, cudaStream_t st, bool verlet = false)
 {
+    verlet = verlet && m->use_verlet && (terms & EHIC_TERM_NONBONDED);
     dim3 grid((unsigned)m->nPx, (unsigned)m->dm.S, (unsigned)R);
     double *gp = want_grad ? m->gprior : nullptr, *pp = want_energy ? m->partP : nullptr;
     KernelTimer kt_(m, KC_PRIOR, st);
@@ -600,16 +621,28 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
     // compact structures go through the cell grid, extended ones through the box-pruned all-pairs sweep;
     // the two kernels take the same per-structure decision from the slice boxes
     const bool cells = m->use_cells && (terms & EHIC_TERM_NONBONDED);
-    m->last_prior_used_cells = cells;
+    m->last_prior_used_cells = cells || verlet;          // partC carries part of the nonbonded energy
     if (terms & EHIC_TERM_NONBONDED) {
         dim3 gb((unsigned)m->dm.n_slices, (unsigned)((long long)R * m->dm.S));
         bbox_kernel<<<gb, 32, 0, st>>>(xs, m->bbox, m->dm.N, m->dm.Np, m->dm.n_slices);
         LAUNCHED();
     }
+    const int *vls = verlet ? m->vl.state : nullptr;
+    if (verlet) {
+        const unsigned n_struct = (unsigned)((long long)R * m->dm.S);
+        verlet_check_kernel<<<n_struct, 256, 0, st>>>(m->dm, m->vl, xs);
+        LAUNCHED();
+        switch (m->prior_threads) {
+        case 64: verlet_build_kernel<64><<<grid, 64, 0, st>>>(m->dm, m->vl, xs, m->r_max, m->bbox); break;
+        case 128: verlet_build_kernel<128><<<grid, 128, 0, st>>>(m->dm, m->vl, xs, m->r_max, m->bbox); break;
+        default: verlet_build_kernel<256><<<grid, 256, 0, st>>>(m->dm, m->vl, xs, m->r_max, m->bbox); break;
+        }
+        LAUNCHED();
+    }
 #define PK(T)                                                                                         \
     do {                                                                                              \
         if (ex) prior_kernel<true, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max, m->bbox, 0);   \
-        else prior_kernel<false, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max, m->bbox, cells ? 1 : 0);     \
+        else prior_kernel<false, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max, m->bbox, cells ? 1 : 0, vls);     \
     } while (0)
     switch (m->prior_threads) {
     case 64: PK(64); break;
@@ -618,6 +651,12 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
     }
 #undef PK
     LAUNCHED();
+    if (verlet) {
+        const int vth = std::min(512, std::max(64, (m->dm.N + 31) / 32 * 32));
+        verlet_force_kernel<<<(unsigned)((long long)R * m->dm.S), vth, 0, st>>>(m->dm, m->vl, xs, d_beta, gp,
+                                                                                 want_energy ? m->partC : nullptr);
+        LAUNCHED();
+    }
     if (cells) {
         dim3 gc((unsigned)m->dm.S, (unsigned)R);
         cell_nonbonded_kernel<<<gc, EHIC_CELL_THREADS, 0, st>>>(m->dm, xs, d_beta, gp, want_energy ? m->partC : nullptr,
@@ -903,7 +942,7 @@ static int enqueue_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, 
         const bool fuse_nb = m->use_tiles && m->nb_fused && !ends;
         const int kpt = fuse_nb ? (prior_terms & ~EHIC_TERM_NONBONDED) : prior_terms;
         if (kpt) {
-            rc = launch_prior(m, R, kpt, m->xs[cur], d_beta, true, ends, st);
+            rc = launch_prior(m, R, kpt, m->xs[cur], d_beta, true, ends, st, true);
             if (rc) return rc;
         }
         GatherArgs ga{};

@@ -479,9 +479,11 @@ template <bool EXACT, int EHIC_PRIOR_THREADS>
 __global__ void __launch_bounds__(EHIC_PRIOR_THREADS)
 prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restrict__ beta,
              double *__restrict__ gprior, double *__restrict__ partP, int terms, double r_max,
-             const double *__restrict__ bbox, int cells_enabled)
+             const double *__restrict__ bbox, int cells_enabled, const int *__restrict__ vl_state = nullptr)
 {
     const int k = blockIdx.y, r = blockIdx.z;
+    // HMC trajectories: structures with a usable Verlet list get their nonbonded term from verlet_force_kernel
+    if (vl_state && vl_state[(long long)r * dm.S + k] != 2) terms &= ~2;
     const int b = blockIdx.x * EHIC_PRIOR_THREADS + threadIdx.x;
     const bool bead_ok = b < dm.N;
     const int bb = bead_ok ? b : dm.N - 1;
@@ -822,6 +824,219 @@ cell_nonbonded_kernel(DevModel dm, const double *__restrict__ xs, const double *
         if (tid == 0) {
             double t = 0.0;
             for (int q = 0; q < EHIC_CELL_THREADS / 32; q++) t += s_red[0][q];
+            partC[rk] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Verlet lists for the nonbonded term inside HMC trajectories (fast mode, N < EHIC_CELL_MAX).
+//
+// The reference rebuilds its neighbour list for every energy and every gradient (forcefields.py:214-224,
+// c/nblist.c).  Along a leapfrog trajectory beads move by a small fraction of their radius per step, so the
+// list is built with a skin -- partners within r_i + r_j + skin -- and reused until some bead of the
+// structure has moved more than skin / 2 from where it was at build time; until then no pair outside the
+// list can be in contact, so the force and energy are exactly those of the all-pairs sweep (same pairs,
+// same ascending partner order, same arithmetic as prior_kernel's fast path).  Everything is decided on
+// the device, per structure, so the trajectory stays one CUDA graph:
+//   verlet_check_kernel   state[rk]: 0 never built, 1 valid, 2 overflow (sticky: prior_kernel keeps the
+//                         structure); stale[rk] = list missing or some bead beyond skin / 2
+//   verlet_build_kernel   stale structures only: thread <-> bead, sweep over all partners (slice boxes
+//                         prune as in prior_kernel), list[bead][slot] ascending, x_ref = x
+//   verlet_force_kernel   CTA <-> structure: gprior += beta * 2k * sum (r_i + r_j - d)^3 / d * (x_o - x_b),
+//                         partC[rk] = sum a^4 over both visits
+#define EHIC_VL_CAP 64
+struct VerletDev {
+    int *state, *stale;     // [R*S]
+    int *cnt;               // [R*S][Np]
+    unsigned short *idx;    // [R*S][Np][EHIC_VL_CAP]: a bead's list is one 128-byte line (N < 4096 fits 16 bits)
+    double *xref;           // [R*S][3][Np]
+    double skin;
+};
+
+__global__ void __launch_bounds__(256)
+verlet_check_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs)
+{
+    const long long rk = blockIdx.x;
+    __shared__ double sh[8];
+    const int st = vl.state[rk];
+    if (st == 2) { if (threadIdx.x == 0) vl.stale[rk] = 0; return; }
+    double mx = 0.0;
+    if (st == 1) {
+        const double *xk = xs + rk * 3LL * dm.Np, *xr = vl.xref + rk * 3LL * dm.Np;
+        for (int b = threadIdx.x; b < dm.N; b += 256) {
+            const double d0 = xk[b] - xr[b], d1 = xk[dm.Np + b] - xr[dm.Np + b], d2 = xk[2 * dm.Np + b] - xr[2 * dm.Np + b];
+            const double d = fma(d2, d2, fma(d1, d1, d0 * d0));
+            mx = fmax(mx, (d == d) ? d : 1e300);       // NaN coordinates: rebuild (and let the sweep see them)
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 1; q < 8; q++) mx = fmax(mx, sh[q]);
+        vl.stale[rk] = (st == 0 || mx > 0.25 * vl.skin * vl.skin) ? 1 : 0;
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+verlet_build_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, double r_max, const double *__restrict__ bbox)
+{
+    const int k = blockIdx.y, r = blockIdx.z;
+    const long long rk = (long long)r * dm.S + k;
+    if (!vl.stale[rk]) return;                                     // CTA-uniform
+    const int b = blockIdx.x * THREADS + threadIdx.x;
+    const bool bead_ok = b < dm.N;
+    const int bb = bead_ok ? b : dm.N - 1;
+    const int Np = dm.Np;
+    const double *xk = xs + rk * 3LL * Np;
+    const double xb0 = xk[bb], xb1 = xk[Np + bb], xb2 = xk[2 * Np + bb];
+    const double rb = dm.radii[bb];
+    __shared__ double2 sxy[EHIC_PRIOR_TILE];
+    __shared__ double2 szr[EHIC_PRIOR_TILE];
+    __shared__ double sbox[EHIC_PRIOR_TILE / 32][6];
+    const double reach = (2.0 * r_max + vl.skin) * (1.0 + 1e-12);
+    const double *bbk = bbox + rk * dm.n_slices * 6;
+    const int my_sl = min((int)((blockIdx.x * THREADS + threadIdx.x) >> 5), dm.n_slices - 1);
+    const double mlo0 = bbk[my_sl * 6] - reach, mlo1 = bbk[my_sl * 6 + 1] - reach, mlo2 = bbk[my_sl * 6 + 2] - reach;
+    const double mhi0 = bbk[my_sl * 6 + 3] + reach, mhi1 = bbk[my_sl * 6 + 4] + reach, mhi2 = bbk[my_sl * 6 + 5] + reach;
+    unsigned short *my_idx = vl.idx + (rk * Np + bb) * (long long)EHIC_VL_CAP;
+    int n = 0;
+    bool over = false;
+    for (int t0 = 0; t0 < dm.N; t0 += EHIC_PRIOR_TILE) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < EHIC_PRIOR_TILE; q += THREADS) {
+            int o = t0 + q;
+            int oo = o < dm.N ? o : dm.N - 1;
+            sxy[q] = make_double2(xk[oo], xk[Np + oo]);
+            szr[q] = make_double2(xk[2 * Np + oo], dm.radii[oo]);
+        }
+        for (int q = threadIdx.x; q < (EHIC_PRIOR_TILE / 32) * 6; q += THREADS) {
+            const int psl = min(t0 / 32 + q / 6, dm.n_slices - 1);
+            sbox[q / 6][q % 6] = bbk[psl * 6 + q % 6];
+        }
+        __syncthreads();
+        const int cnt = min(EHIC_PRIOR_TILE, dm.N - t0);
+        for (int q0 = 0; q0 < cnt; q0 += 32) {
+            const double *pb = sbox[q0 >> 5];
+            if (pb[0] > mhi0 || pb[3] < mlo0 || pb[1] > mhi1 || pb[4] < mlo1 || pb[2] > mhi2 || pb[5] < mlo2) continue;
+            const int qe = min(32, cnt - q0);
+            for (int qq = 0; qq < qe; qq++) {
+                const double2 pxy = sxy[q0 + qq], pzr = szr[q0 + qq];
+                const double dx = pxy.x - xb0, dy = pxy.y - xb1, dz = pzr.x - xb2;
+                const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                const double lim = rb + pzr.y + vl.skin;
+                const int o = t0 + q0 + qq;
+                if (!(s2 >= lim * lim) && o != b && bead_ok) {      // !(>=): NaN distances are listed, like the sweep would see them
+                    if (n < EHIC_VL_CAP) my_idx[n] = (unsigned short)o;
+                    else over = true;
+                    n++;
+                }
+            }
+        }
+    }
+    if (bead_ok) {
+        vl.cnt[rk * Np + b] = min(n, EHIC_VL_CAP);
+        double *xr = vl.xref + rk * 3LL * Np;
+        xr[b] = xb0; xr[Np + b] = xb1; xr[2 * Np + b] = xb2;
+    }
+    if (over) atomicExch(&vl.state[rk], 2);                        // integer flag: same outcome in any order
+}
+
+__global__ void __launch_bounds__(512)
+verlet_force_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, const double *__restrict__ beta,
+                    double *__restrict__ gprior, double *__restrict__ partC)
+{
+    const long long rk = blockIdx.x;
+    const int r = (int)(rk / dm.S);
+    __shared__ double sh[32];
+    const int nth = blockDim.x;                                    // one pass over the beads when N <= 1024
+    __shared__ int s_bin[EHIC_VL_CAP + 2];
+    __shared__ short s_perm[EHIC_CELL_MAX];                        // N < EHIC_CELL_MAX on this path
+    const int st = vl.state[rk];
+    if (st == 2) {                                                 // prior_kernel evaluated this structure
+        if (partC && threadIdx.x == 0) partC[rk] = 0.0;
+        return;
+    }
+    const int Np = dm.Np, N = dm.N;
+    const double *xk = xs + rk * 3LL * Np;
+    const int *cnt = vl.cnt + rk * Np;
+    const unsigned short *idx = vl.idx + rk * (long long)Np * EHIC_VL_CAP;
+    const double sc = (beta ? beta[r] : 1.0) * (dm.k_nb * 2.0);
+    // The kernel is latency bound (index -> coordinates -> arithmetic, a dozen times per bead), so the beads are
+    // handed out sorted by list length (counting sort, longest first): the lanes of a warp then finish together.
+    // Which thread takes which bead affects no gradient element; when the energy is wanted (first and last step
+    // of a trajectory) the beads keep their natural order so that the energy sum has a fixed order too.
+    const bool sorted = partC == nullptr;
+    if (sorted) {
+        for (int q = threadIdx.x; q < EHIC_VL_CAP + 2; q += nth) s_bin[q] = 0;
+        __syncthreads();
+        for (int b = threadIdx.x; b < N; b += nth) atomicAdd(&s_bin[EHIC_VL_CAP - cnt[b] + 1], 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int run = 0;
+            for (int q = 1; q < EHIC_VL_CAP + 2; q++) { const int c = s_bin[q]; s_bin[q] = run; run += c; }
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < N; b += nth) s_perm[atomicAdd(&s_bin[EHIC_VL_CAP - cnt[b] + 1], 1)] = (short)b;
+        __syncthreads();
+    }
+    double e_nb = 0.0;
+    for (int t = threadIdx.x; t < N; t += nth) {
+        const int b = sorted ? (int)s_perm[t] : t;
+        const double xb0 = xk[b], xb1 = xk[Np + b], xb2 = xk[2 * Np + b];
+        const double rb = dm.radii[b];
+        const int n = cnt[b];
+        const uint4 *row = reinterpret_cast<const uint4 *>(idx + (long long)b * EHIC_VL_CAP);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        // ascending partner order, as in prior_kernel.  The whole list of a bead is one cache line: 8 partner
+        // indices per 16-byte load, then the coordinates of 2 partners in flight at a time.
+        for (int u0 = 0; u0 < n; u0 += 8) {
+            const uint4 w = row[u0 >> 3];
+            const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int h = 0; h < 4; h++) {
+                const int ub = u0 + 2 * h;
+                if (ub < n) {
+                    const int o[2] = {(int)(ws[h] & 0xffffu), (int)(ws[h] >> 16)};
+                    double px[2], py[2], pz[2], pr[2];
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int oo = (ub + q < n) ? o[q] : b;          // slots past the end of the list are undefined
+                        px[q] = xk[oo]; py[q] = xk[Np + oo]; pz[q] = xk[2 * Np + oo]; pr[q] = dm.radii[oo];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const double dx = px[q] - xb0, dy = py[q] - xb1, dz = pz[q] - xb2;
+                        const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                        const double d0 = rb + pr[q];
+                        if (ub + q < n && s2 < d0 * d0) {
+                            const double rd = rsqrt_nr(s2);
+                            const double a = d0 - s2 * rd, aa = a * a;
+                            const double g = aa * a * rd;
+                            a0 = fma(g, dx, a0); a1 = fma(g, dy, a1); a2 = fma(g, dz, a2);
+                            e_nb += aa * aa;
+                        }
+                    }
+                }
+            }
+        }
+        if (gprior) {
+            double *o = gprior + (rk * N + b) * 3;
+            o[0] = fma(sc, a0, o[0]); o[1] = fma(sc, a1, o[1]); o[2] = fma(sc, a2, o[2]);
+        }
+    }
+    if (threadIdx.x == 0 && st == 0) vl.state[rk] = 1;             // built in this step without overflow
+    if (partC) {
+        e_nb = warp_sum(e_nb);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = e_nb;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int q = 0; q < (nth >> 5); q++) t += sh[q];
             partC[rk] = t;
         }
     }

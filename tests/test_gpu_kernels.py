@@ -480,6 +480,50 @@ def test_one_launch_trajectory_equals_multi_kernel_trajectory(monkeypatch, S, N,
     np.testing.assert_allclose(res["small"][2], res["multi"][2], rtol=1e-11)
 
 
+# ---- Verlet lists inside trajectories ---------------------------------------------------------------
+
+@pytest.mark.parametrize("scenario", ["chain", "tiny_skin", "overflow"])
+def test_verlet_list_trajectory_equals_all_pairs_trajectory(monkeypatch, scenario):
+    """the nonbonded term of a multi-kernel trajectory comes from Verlet lists reused across leapfrog steps;
+    the trajectory must be the one the all-pairs sweep gives (rebuilds forced by a tiny skin; a ball of
+    beads with more than 64 neighbours each exercises the overflow fallback)"""
+    import torch
+    from ensemble_hic_b200.engine import launch_count
+    monkeypatch.setenv("EHIC_TRAJ", "multi")
+    monkeypatch.setenv("EHIC_PATH", "rows")
+    if scenario == "tiny_skin":
+        monkeypatch.setenv("EHIC_VERLET_SKIN", "0.02")
+    S, N = 3, 150
+    pb = make_problem(seed=11, S=S, N=N, density=0.2, step=0.8)
+    X0 = pb["X"]
+    if scenario == "overflow":
+        X0 = np.stack([_ball(np.random.default_rng(k), N, 1.2) for k in range(S)])     # everybody touches everybody
+    R, L = 2, 60
+    rng = np.random.default_rng(0)
+    X = np.stack([X0, X0 + rng.normal(scale=0.02, size=X0.shape)]).reshape(R, -1)
+    P = rng.normal(size=X.shape)
+    norm = np.array([2.5, 3.5]); lam = np.array([0.3, 1.0]); bet = np.array([0.5, 1.0])
+    eps = np.array([2e-3, 4e-3]) if scenario != "overflow" else np.array([2e-4, 4e-4])
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    res = {}
+    for verlet in ("1", "0"):
+        monkeypatch.setenv("EHIC_VERLET", verlet)
+        m = _model(pb, False, max_replicas=R)
+        x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
+        l0 = launch_count()
+        for _ in range(2):                               # second trajectory starts from a list built in the first
+            m.hmc_trajectory_device(R, L, x_t, p_t, t(norm), t(lam), t(bet), t(eps), H_t)
+        torch.cuda.synchronize()
+        res[verlet] = (x_t.cpu().numpy(), p_t.cpu().numpy(), H_t.cpu().numpy(), launch_count() - l0)
+        m.close()
+    assert res["1"][3] > res["0"][3]                      # the list kernels did run
+    assert relerr(res["1"][0], res["0"][0]) < 1e-12
+    assert relerr(res["1"][1], res["0"][1]) < 1e-10
+    np.testing.assert_allclose(res["1"][2], res["0"][2], rtol=1e-11)
+    assert np.all(np.isfinite(res["1"][2]))
+
+
 # ---- cell-grid nonbonded path ------------------------------------------------------------------------
 
 def _ball(rng, n, radius):
