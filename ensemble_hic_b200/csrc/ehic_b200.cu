@@ -373,7 +373,8 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     {   // Verlet lists (trajectories only): fast mode, all-pairs regime, bounded memory
         const char *ve = getenv("EHIC_VERLET");
         const size_t idx_bytes = sizeof(unsigned short) * Rm * S * (size_t)EHIC_VL_CAP * dm.Np;
-        m->use_verlet = !exact && !m->use_cells && N >= 32 && desc->nonbonded_k != 0.0 && !(ve && !strcmp(ve, "0")) &&
+        m->use_verlet = !exact && !m->use_cells && N >= 32 && N < EHIC_CELL_MAX && desc->nonbonded_k != 0.0 &&
+                        !(ve && !strcmp(ve, "0")) &&
                         idx_bytes <= ((size_t)8 << 30);
         if (m->use_verlet) {
             const char *sk = getenv("EHIC_VERLET_SKIN");
