@@ -1261,14 +1261,7 @@ __device__ __forceinline__ void reduce8(double (&r)[8], int lane);      // defin
 // warp with ONE halving butterfly (reduce8) per batch, and after 4 batches every lane finishes one
 // pair (mock count, Poisson weight into both CSR slots, log-likelihood term).  Bead i of
 // consecutive pairs is the same most of the time and stays in registers.
-#ifndef EHIC_LANE_FWD_MINB
-#define EHIC_LANE_FWD_MINB 3
-#endif
-#ifndef EHIC_LANE_UNROLL
-#define EHIC_LANE_UNROLL 8
-#endif
-constexpr int kLaneUnroll = EHIC_LANE_UNROLL;
-__global__ void __launch_bounds__(256, EHIC_LANE_FWD_MINB)
+__global__ void __launch_bounds__(256, 3)       // 80 registers: 24 warps per SM hide the L2 latency of the partner rows better than 16
 forward_lane_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, const double *__restrict__ norm,
                     double *__restrict__ md_out, double *__restrict__ wbuf,
                     double *__restrict__ partA, int want_logl)
@@ -1377,7 +1370,7 @@ backward_lane_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
         const long long e0 = ld.row_off[b], e1 = ld.row_off[b + 1];
         const double *wr = ga.wbuf + (long long)r * dm.wstride;
         const double alpha = dm.alpha;
-#pragma unroll kLaneUnroll
+#pragma unroll 4
         for (long long e = e0; e < e1; e++) {
             const int4 v = __ldg(reinterpret_cast<const int4 *>(ld.ent + e));
             const double dc = __hiloint2double(v.y, v.x);
