@@ -23,7 +23,7 @@ def cfg_d():
     return _config_d()
 
 
-def _model(pb, monkeypatch=None, path=None, exact=False, R=1):
+def _model(pb, monkeypatch=None, path=None, exact=False, R=1, fp32=False):
     from ensemble_hic_b200.engine import Model
     import os
     if path is None:
@@ -32,24 +32,29 @@ def _model(pb, monkeypatch=None, path=None, exact=False, R=1):
         os.environ["EHIC_PATH"] = path
     try:
         return Model(pb["S"], pb["radii"], pb["data"], pb["cds"], alpha=10.0, k_nb=500.0, k_bb=500.0,
-                     exact=exact, max_replicas=R)
+                     exact=exact, max_replicas=R, fp32=fp32)
     finally:
         os.environ.pop("EHIC_PATH", None)
 
 
 def test_config_d_paths_and_modes_agree(cfg_d):
-    """tile path == row path == exact (reference-order, IEEE) arithmetic at full size"""
+    """tile path == lane path == row path == exact (reference-order, IEEE) arithmetic at full size;
+    the optional FP32 mode stays within its 1e-5"""
     pb = cfg_d
-    tiles, rows, exact = _model(pb), _model(pb, path="rows"), _model(pb, exact=True)
-    assert tiles.info()["path"] == "tiles" and rows.info()["path"] != "tiles"
+    tiles, lanes, rows, exact = _model(pb), _model(pb, path="lanes"), _model(pb, path="rows"), _model(pb, exact=True)
+    fp32 = _model(pb, fp32=True)
+    assert tiles.info()["path"] == "tiles" and lanes.info()["path"] == "lanes" and rows.info()["path"] == "rows"
     out = {}
-    for name, m in (("tiles", tiles), ("rows", rows), ("exact", exact)):
+    for name, m in (("tiles", tiles), ("lanes", lanes), ("rows", rows), ("exact", exact), ("fp32", fp32)):
         out[name] = m.evaluate(pb["X"], 3.0, 0.7, 0.4, energies=True, md=True)
         m.close()
-    for a in ("tiles", "rows"):
+    for a in ("tiles", "lanes", "rows"):
         assert relerr(out[a]["grad"], out["exact"]["grad"]) < 1e-12
         assert relerr(out[a]["md"], out["exact"]["md"]) < 1e-12
         np.testing.assert_allclose(out[a]["energies"], out["exact"]["energies"], rtol=1e-11)
+    assert relerr(out["fp32"]["grad"], out["exact"]["grad"]) < 1e-5
+    np.testing.assert_allclose(out["fp32"]["md"], out["exact"]["md"], rtol=2e-5)
+    np.testing.assert_allclose(out["fp32"]["energies"], out["exact"]["energies"], rtol=1e-5)
 
 
 def test_config_d_invariances_and_directional_derivative(cfg_d):
