@@ -10,6 +10,7 @@ FLAG_EXACT, FLAG_FP32, FLAG_NB_CELLS = 1, 2, 4
 (PARAM_ALPHA, PARAM_NONBONDED_K, PARAM_BACKBONE_K, PARAM_SPHERE_RADIUS, PARAM_SPHERE_K,
  PARAM_SPHERE_CX, PARAM_SPHERE_CY, PARAM_SPHERE_CZ) = range(8)
 N_ENERGIES = 4
+E_LIKELIHOOD, E_NONBONDED, E_BACKBONE, E_SPHERE = 0, 1, 2, 3     # EHIC_E_* indices of the energy vector
 
 _dp = C.POINTER(C.c_double)
 _i64p = C.POINTER(C.c_int64)

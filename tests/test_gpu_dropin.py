@@ -272,6 +272,35 @@ def test_run_simulation_and_continuation_single_gpu(hairpin, tmp_path):
     assert np.isfinite(first.variables["structures"]).all()
 
 
+def test_batch_reevaluation_of_stored_samples(hairpin, tmp_path):
+    """the energy table calculate_DOS builds (analysis_functions.py:440-458), from the stored
+    samples of a finished run, batched on the GPU -- against the per-sample, per-component evaluation"""
+    from ensemble_hic_b200 import reevaluation, run_simulation
+    from ensemble_hic_b200.setup_functions import make_posterior, parse_config_file
+    cfg, g = hairpin
+    txt = open(cfg).read().replace("n_replicas = 2", "n_replicas = 3").replace("samples_dump_interval = 100", "samples_dump_interval = 20") \
+                          .replace("samples_dump_step = 20", "samples_dump_step = 5").replace("timestep = 1e-4", "timestep = 1e-3")
+    open(cfg, "w").write(txt)
+    run_simulation.main([cfg, "--n-samples", "60", "--quiet", "--seed", "5"])
+    energies, sels = reevaluation.replica_energies(cfg, 60, 2, 20, max_replicas=3, rng=np.random.default_rng(0))
+    assert energies.shape == (3, 4, 2) and sels.shape == (3, 4)          # 8 stored samples after burn-in, half of them
+    settings = parse_config_file(cfg)
+    p = make_posterior(settings)
+    L, P = p.likelihoods["ensemble_contacts"], p.priors["nonbonded_prior"]
+    out = str(tmp_path / "out") + "/"
+    for r in range(3):
+        samples = reevaluation.load_sr_samples(out + "samples/", r + 1, 61, 20, 20)
+        assert len(samples) == 8
+        for q, idx in enumerate(sels[r]):
+            x = samples[idx]
+            ref = [-L.log_prob(**x.variables), -P.log_prob(structures=x.variables["structures"])]
+            np.testing.assert_allclose(energies[r, q], ref, rtol=1e-11)
+    sched = {"lammda": np.linspace(0, 1, 3), "beta": np.linspace(0.001, 1, 3)}
+    qm = reevaluation.reweighting_matrix(energies, sched)
+    assert qm.shape == (3, 12)
+    np.testing.assert_allclose(qm[1], 0.5 * energies.reshape(-1, 2)[:, 0] + sched["beta"][1] * energies.reshape(-1, 2)[:, 1])
+
+
 def test_api_errors():
     from ensemble_hic_b200 import _lib
     from ensemble_hic_b200.engine import Model

@@ -305,3 +305,26 @@ def test_swap_decisions_use_energies_only():
     assert works[0] == pytest.approx((E(0, b) - E(0, a)) + (E(1, a) - E(1, b))) == pytest.approx(w)
     assert acc[0] == (np.log(0.999999) < -w)
     assert decide_swaps([(0, 1)], slot_of_temp, np.full((3, 2), np.nan), lam, bet, [0.5])[0] == [False]
+
+
+def test_stored_sample_loader_and_reweighting_matrix(tmp_path):
+    """host side of the batch re-evaluation (reference: analysis_functions.py:38-73, 460-464)"""
+    import pickle
+    from ensemble_hic_b200 import reevaluation
+    from ensemble_hic_b200._binf import BinfState
+    folder = str(tmp_path) + "/"
+    for first in range(0, 100, 20):                       # dump interval 20, dump step 5: 4 states per file
+        states = [BinfState({"structures": np.full(6, first + q), "norm": 1.0 + first + q}) for q in (0, 5, 10, 15)]
+        with open(folder + "samples_replica2_%d-%d.pickle" % (first, first + 20), "wb") as f:
+            pickle.dump(states, f)
+    s = reevaluation.load_sr_samples(folder, 2, 101, 20, 40)
+    assert [x.variables["norm"] for x in s] == [1.0 + v for v in (40, 45, 50, 55, 60, 65, 70, 75, 80, 85, 90, 95)]
+    s = reevaluation.load_sr_samples(folder, 2, 101, 20, 5, interval=2)      # burn-in below one file: skip 5 states
+    assert len(s) == (20 - 5 + 1) // 2 and s[0].variables["norm"] == 1.0 + 25
+    E = np.arange(12.0).reshape(2, 3, 2)
+    q = reevaluation.reweighting_matrix(E, {"lammda": [0.0, 1.0], "beta": [0.5, 1.0]})
+    assert q.shape == (2, 6)
+    np.testing.assert_allclose(q[0], 0.5 * E.reshape(-1, 2)[:, 1])
+    np.testing.assert_allclose(q[1], E.reshape(-1, 2).sum(1))
+    q = reevaluation.reweighting_matrix(E, {"beta": [0.5, 1.0]})
+    np.testing.assert_allclose(q[1], E.reshape(-1, 2)[:, 1])
