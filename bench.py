@@ -349,6 +349,37 @@ def run_b200(args):
         m32.close()
         del g32
 
+    # ---- the reference's production shape beside the headline (not the bench workload): nora2012, 308 beads x
+    # 30 structures, sparse list M = 10 145, the full 302-replica ladder on this one GPU, one HMC trajectory --------
+    other = None
+    gold = os.path.join(ROOT, "tests", "golden", "nora2012.npz")
+    if rank == 0 and world == 1 and os.path.exists(gold) and not args.no_extras:
+        gn = np.load(gold)
+        Rn, Ln = 302, 50
+        mn = Model(int(gn["S"]), gn["radii"], gn["data"], gn["cds"], alpha=float(gn["alpha"]), k_nb=float(gn["k_nb"]),
+                   k_bb=float(gn["k_bb"]), max_replicas=Rn, device=local)
+        rs = np.random.default_rng(0)
+        tn = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device=dev)
+        xn = tn(np.stack([gn["X"] + 0.01 * rs.normal(size=gn["X"].shape) for _ in range(Rn)]).reshape(Rn, -1))
+        pn = tn(rs.normal(size=tuple(xn.shape)))
+        ladn = tn(np.linspace(0.05, 1.0, Rn)); epsn = tn(np.full(Rn, 1e-4)); nrmn = tn(np.full(Rn, float(gn["norm"])))
+        Hn = torch.zeros(Rn, 4, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            mn.hmc_trajectory_device(Rn, Ln, xn, pn, nrmn, ladn, ladn, epsn, Hn)
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(3):
+            mn.hmc_trajectory_device(Rn, Ln, xn, pn, nrmn, ladn, ladn, epsn, Hn)
+        b1.record()
+        torch.cuda.synchronize()
+        msn = b0.elapsed_time(b1) / 3
+        other = {"nora2012_302_replicas": {"path": mn.info()["path"], "trajectory_length": Ln,
+                                           "ms_per_leapfrog_step": msn / (Ln + 1),
+                                           "replica_grad_evals_per_s": Rn * (Ln + 1) / (msn * 1e-3)}}
+        mn.close()
+        del xn, pn
+
     # ---- per-kernel durations (CUDA events on the launching stream, same call sequence) ------
     kern = None
     if rank == 0:
@@ -398,7 +429,7 @@ def run_b200(args):
                         "d2h_bytes_per_step": bytes_x,
                         "api": "ehic_evaluate_host (C ABI) with pinned host buffers, batched over the GPU's replicas"},
                 "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "re_sweeps": sweeps,
-                "fp32_mode": fp32_mode}
+                "fp32_mode": fp32_mode, "other_workloads": other}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -412,6 +443,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the nora2012-shape trajectory timing")
     ap.add_argument("--sweeps", type=int, default=5, help="RE iterations timed for the sweeps/s figure (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
