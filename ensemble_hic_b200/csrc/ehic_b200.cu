@@ -93,6 +93,7 @@ struct ehic_model {
     cudaStream_t st_stream = nullptr, st_stream2 = nullptr, st_in = nullptr, st_out = nullptr;
     static constexpr int kMaxChunks = 8;
     cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // trajectory: prior kernels run beside the forward kernel
     // per-replica strides (elements) of the workspace arrays, for evaluating a chunk in replica slots [s, s+n)
     struct WsStrides { size_t xs = 0, xt = 0, wbuf = 0, tw = 0, gprior = 0, bbox = 0, partC = 0, partA = 0, partP = 0,
                        partK = 0, Grow = 0, Pbuf = 0, cell = 0; } wss;
@@ -457,6 +458,8 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     for (int q = 0; ok && q < ehic_model::kMaxChunks; q++)
         ok = cudaEventCreateWithFlags(&m->ev_in[q], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&m->ev_done[q], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "stream / event creation failed"); }
     *out = m;
     return EHIC_OK;
@@ -471,6 +474,8 @@ int ehic_model_destroy(ehic_model_t *m)
     cudaFree(m->st_x); cudaFree(m->st_g); cudaFree(m->st_md); cudaFree(m->st_small);
     if (m->st_stream) cudaStreamDestroy(m->st_stream);
     if (m->st_stream2) cudaStreamDestroy(m->st_stream2);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     if (m->st_in) cudaStreamDestroy(m->st_in);
     if (m->st_out) cudaStreamDestroy(m->st_out);
     for (int q = 0; q < ehic_model::kMaxChunks; q++) { if (m->ev_in[q]) cudaEventDestroy(m->ev_in[q]); if (m->ev_done[q]) cudaEventDestroy(m->ev_done[q]); }
@@ -933,18 +938,31 @@ static int enqueue_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, 
     if (!m->dm.sphere_active) prior_terms &= ~EHIC_TERM_SPHERE;
     rc = launch_pack(m, R, d_x, m->xs[0], m->xt[0], st);
     if (rc) return rc;
+    // The prior kernels (nonbonded lists, backbone, sphere) only need the positions: they run on a side stream
+    // beside the forward kernel and join before the backward / gather kernel (parallel branches of the graph).
+    static const bool fork_env = []() { const char *e = getenv("EHIC_FORK"); return !(e && !strcmp(e, "0")); }();
+    const bool fork = fork_env && st != m->st_stream2;
+    cudaStream_t side = fork ? m->st_stream2 : st;
     int cur = 0;
     for (int s = 0; s <= n_steps; s++) {
         const bool first = (s == 0), last = (s == n_steps);
         const bool ends = first || last;
         m->cur_xt = cur;
-        rc = launch_forward(m, R, m->xs[cur], d_norm, nullptr, true, ends, st, d_lammda);
-        if (rc) return rc;
         const bool fuse_nb = m->use_tiles && m->nb_fused && !ends;
         const int kpt = fuse_nb ? (prior_terms & ~EHIC_TERM_NONBONDED) : prior_terms;
+        if (fork && kpt) {
+            CU(cudaEventRecord(m->ev_fork, st));
+            CU(cudaStreamWaitEvent(side, m->ev_fork, 0));
+        }
+        rc = launch_forward(m, R, m->xs[cur], d_norm, nullptr, true, ends, st, d_lammda);
+        if (rc) return rc;
         if (kpt) {
-            rc = launch_prior(m, R, kpt, m->xs[cur], d_beta, true, ends, st, true);
+            rc = launch_prior(m, R, kpt, m->xs[cur], d_beta, true, ends, side, true);
             if (rc) return rc;
+            if (fork) {
+                CU(cudaEventRecord(m->ev_join, side));
+                CU(cudaStreamWaitEvent(st, m->ev_join, 0));
+            }
         }
         GatherArgs ga{};
         ga.xt = m->xt[cur]; ga.xs_cur = m->xs[cur]; ga.wbuf = m->wbuf; ga.lammda = d_lammda; ga.gprior = kpt ? m->gprior : nullptr;
