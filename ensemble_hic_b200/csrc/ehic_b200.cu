@@ -69,6 +69,7 @@ struct ehic_model {
     double *wbuf = nullptr, *gprior = nullptr, *bbox = nullptr, *partC = nullptr;
     int *cell_list = nullptr;
     bool use_cells = false;         // fast mode: nonbonded term through the per-structure cell grid
+    bool in_host_pipeline = false;  // ehic_evaluate_host is enqueueing chunks on the two compute streams
     bool use_verlet = false;        // HMC trajectories: nonbonded term from Verlet lists reused across leapfrog steps
     VerletDev vl{};
     double *partA = nullptr, *partP = nullptr, *partK = nullptr;
@@ -816,17 +817,31 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     if (rc) return rc;
     m->cur_xt = 0;
     const bool need_forward = (lik && (d_grad || d_energies)) || d_md;
-    if (need_forward) {
-        rc = launch_forward(m, R, m->xs[0], d_norm, d_md, lik && d_grad, lik && d_energies, st, d_lammda);
-        if (rc) return rc;
-    }
     // pure gradient calls on the tile path evaluate the nonbonded force inside the backward tile kernel
     const bool fuse_nb = m->use_tiles && m->nb_fused && lik && (terms & EHIC_TERM_NONBONDED) && d_grad && !d_energies;
     const int kernel_prior_terms = fuse_nb ? (prior_terms & ~EHIC_TERM_NONBONDED) : prior_terms;
     const bool need_prior = kernel_prior_terms && (d_grad || d_energies);
-    if (need_prior) {
-        rc = launch_prior(m, R, kernel_prior_terms, m->xs[0], d_beta, d_grad != nullptr, d_energies != nullptr, st);
+    // the prior kernels only need the packed positions: beside the forward kernel, on a side stream
+    static const bool fork_env = []() { const char *e = getenv("EHIC_FORK"); return !(e && !strcmp(e, "0")); }();
+    // (not under per-kernel profiling, whose event pairs assume one stream, and not inside the host pipeline,
+    // whose chunks already keep both compute streams busy)
+    const bool fork = fork_env && need_forward && need_prior && !m->profiling && !m->in_host_pipeline;
+    cudaStream_t side = !fork ? st : (st == m->st_stream2 ? m->st_stream : m->st_stream2);
+    if (fork) {
+        CU(cudaEventRecord(m->ev_fork, st));
+        CU(cudaStreamWaitEvent(side, m->ev_fork, 0));
+    }
+    if (need_forward) {
+        rc = launch_forward(m, R, m->xs[0], d_norm, d_md, lik && d_grad, lik && d_energies, st, d_lammda);
         if (rc) return rc;
+    }
+    if (need_prior) {
+        rc = launch_prior(m, R, kernel_prior_terms, m->xs[0], d_beta, d_grad != nullptr, d_energies != nullptr, side);
+        if (rc) return rc;
+        if (fork) {
+            CU(cudaEventRecord(m->ev_join, side));
+            CU(cudaStreamWaitEvent(st, m->ev_join, 0));
+        }
     }
     if (d_grad) {
         GatherArgs ga{};
@@ -941,7 +956,7 @@ static int enqueue_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, 
     // The prior kernels (nonbonded lists, backbone, sphere) only need the positions: they run on a side stream
     // beside the forward kernel and join before the backward / gather kernel (parallel branches of the graph).
     static const bool fork_env = []() { const char *e = getenv("EHIC_FORK"); return !(e && !strcmp(e, "0")); }();
-    const bool fork = fork_env && st != m->st_stream2;
+    const bool fork = fork_env && st != m->st_stream2 && !m->profiling;
     cudaStream_t side = fork ? m->st_stream2 : st;
     int cur = 0;
     for (int s = 0; s <= n_steps; s++) {
@@ -1099,10 +1114,12 @@ int ehic_evaluate_host(ehic_model_t *m, int R, int terms, const double *h_x, con
         CU(cudaStreamWaitEvent(st, m->ev_in[c], 0));
         {
             SlotShift shift(m, r0);
+            m->in_host_pipeline = true;
             rc = ehic_evaluate(m, r1 - r0, terms, m->st_x + r0 * per, h_norm ? d_norm + r0 : nullptr,
                                h_lammda ? d_lam + r0 : nullptr, h_beta ? d_bet + r0 : nullptr,
                                h_grad ? m->st_g + r0 * per : nullptr, h_energies ? d_E + 4 * (size_t)r0 : nullptr,
                                h_md ? m->st_md + r0 * M : nullptr, st);
+            m->in_host_pipeline = false;
         }
         if (rc) { cudaDeviceSynchronize(); return rc; }
         CU(cudaEventRecord(m->ev_done[c], st));
