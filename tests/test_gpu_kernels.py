@@ -524,6 +524,37 @@ def test_verlet_list_trajectory_equals_all_pairs_trajectory(monkeypatch, scenari
     assert np.all(np.isfinite(res["1"][2]))
 
 
+def test_verlet_lists_survive_changing_batch_sizes(monkeypatch):
+    """the lists belong to replica slots: calls with fewer replicas than max_replicas, then more, then other
+    coordinates in the same slots, must all give the all-pairs result"""
+    import torch
+    monkeypatch.setenv("EHIC_TRAJ", "multi")
+    pb = make_problem(seed=21, S=4, N=90, density=0.3, step=0.8)
+    rng = np.random.default_rng(3)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device=dev)
+    calls = []
+    for R in (2, 4, 3, 4):
+        X = np.stack([pb["X"] + rng.normal(scale=0.3, size=pb["X"].shape) for _ in range(R)]).reshape(R, -1)
+        calls.append((R, X, rng.normal(size=X.shape)))
+    res = {}
+    for verlet in ("1", "0"):
+        monkeypatch.setenv("EHIC_VERLET", verlet)
+        m = _model(pb, False, max_replicas=4)
+        out = []
+        for R, X, P in calls:
+            x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
+            m.hmc_trajectory_device(R, 8, x_t, p_t, t(np.full(R, 3.0)), t(np.linspace(0.2, 1, R)), t(np.linspace(1, 0.2, R)),
+                                    t(np.full(R, 2e-3)), H_t)
+            torch.cuda.synchronize()
+            out.append((x_t.cpu().numpy(), p_t.cpu().numpy(), H_t.cpu().numpy()))
+        res[verlet] = out
+        m.close()
+    for a, b in zip(res["1"], res["0"]):
+        assert relerr(a[0], b[0]) < 1e-12 and relerr(a[1], b[1]) < 1e-10
+        np.testing.assert_allclose(a[2], b[2], rtol=1e-11)
+
+
 # ---- cell-grid nonbonded path ------------------------------------------------------------------------
 
 def _ball(rng, n, radius):
