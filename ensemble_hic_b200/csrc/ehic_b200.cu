@@ -95,6 +95,10 @@ struct ehic_model {
     static constexpr int kMaxChunks = 8;
     cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // trajectory: prior kernels run beside the forward kernel
+    // single evaluations: compute lane 0 = the caller's stream / st_stream, lane 1 = st_stream2; each lane has its
+    // own side stream for the prior kernels
+    cudaStream_t st_side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork_l[2] = {nullptr, nullptr}, ev_join_l[2] = {nullptr, nullptr}, ev_half = nullptr, ev_half_done = nullptr;
     // per-replica strides (elements) of the workspace arrays, for evaluating a chunk in replica slots [s, s+n)
     struct WsStrides { size_t xs = 0, xt = 0, wbuf = 0, tw = 0, gprior = 0, bbox = 0, partC = 0, partA = 0, partP = 0,
                        partK = 0, Grow = 0, Pbuf = 0, cell = 0; } wss;
@@ -460,7 +464,13 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         ok = cudaEventCreateWithFlags(&m->ev_in[q], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&m->ev_done[q], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) == cudaSuccess;
+         cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&m->ev_half, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&m->ev_half_done, cudaEventDisableTiming) == cudaSuccess;
+    for (int q = 0; ok && q < 2; q++)
+        ok = cudaStreamCreateWithFlags(&m->st_side[q], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&m->ev_fork_l[q], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&m->ev_join_l[q], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "stream / event creation failed"); }
     *out = m;
     return EHIC_OK;
@@ -477,6 +487,13 @@ int ehic_model_destroy(ehic_model_t *m)
     if (m->st_stream2) cudaStreamDestroy(m->st_stream2);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->ev_half) cudaEventDestroy(m->ev_half);
+    if (m->ev_half_done) cudaEventDestroy(m->ev_half_done);
+    for (int q = 0; q < 2; q++) {
+        if (m->st_side[q]) cudaStreamDestroy(m->st_side[q]);
+        if (m->ev_fork_l[q]) cudaEventDestroy(m->ev_fork_l[q]);
+        if (m->ev_join_l[q]) cudaEventDestroy(m->ev_join_l[q]);
+    }
     if (m->st_in) cudaStreamDestroy(m->st_in);
     if (m->st_out) cudaStreamDestroy(m->st_out);
     for (int q = 0; q < ehic_model::kMaxChunks; q++) { if (m->ev_in[q]) cudaEventDestroy(m->ev_in[q]); if (m->ev_done[q]) cudaEventDestroy(m->ev_done[q]); }
@@ -806,6 +823,33 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     int rc = check_call(m, R);
     if (rc) return rc;
     if (!d_x) return fail(EHIC_ERR_INVALID, "null coordinates");
+    {   // Large batches run as two halves side by side (second half on st_stream2, in its own workspace slots):
+        // the CTAs of one half fill the partial last waves of the other's kernels.  Measured at config D:
+        // 1128 -> 1141 grad evals/s; four parts: 1134.  Only when a half is still a large launch.
+        static const int split_env = []() { const char *e = getenv("EHIC_SPLIT"); return e ? atoi(e) : -1; }();
+        cudaStream_t st0 = (cudaStream_t)stream;
+        const bool heavy = (double)m->dm.S * (double)m->dm.M * (R / 2) >= 2e8;
+        const int parts = split_env >= 0 ? split_env : (heavy ? 2 : 1);
+        if (parts >= 2 && R >= 2 * parts && !m->in_host_pipeline && !m->profiling && st0 != m->st_stream2) {
+            const size_t per = (size_t)m->dm.S * m->dm.N * 3;
+            m->in_host_pipeline = true;
+            CU(cudaEventRecord(m->ev_half, st0));
+            CU(cudaStreamWaitEvent(m->st_stream2, m->ev_half, 0));
+            for (int c = 0; c < parts && rc == EHIC_OK; c++) {
+                const int r0 = (int)((long long)R * c / parts), r1 = (int)((long long)R * (c + 1) / parts);
+                SlotShift shift(m, r0);
+                rc = ehic_evaluate(m, r1 - r0, terms, d_x + r0 * per, d_norm ? d_norm + r0 : nullptr, d_lammda ? d_lammda + r0 : nullptr,
+                                   d_beta ? d_beta + r0 : nullptr, d_grad ? d_grad + r0 * per : nullptr,
+                                   d_energies ? d_energies + 4 * (size_t)r0 : nullptr, d_md ? d_md + (size_t)r0 * m->dm.M : nullptr,
+                                   (c & 1) ? m->st_stream2 : st0);
+            }
+            m->in_host_pipeline = false;
+            if (rc) return rc;
+            CU(cudaEventRecord(m->ev_half_done, m->st_stream2));
+            CU(cudaStreamWaitEvent(st0, m->ev_half_done, 0));
+            return EHIC_OK;
+        }
+    }
     terms &= EHIC_TERM_ALL;
     if (!m->dm.sphere_active) terms &= ~EHIC_TERM_SPHERE;
     if (m->dm.M == 0) terms &= ~EHIC_TERM_LIKELIHOOD;         // no data points: the likelihood term is vacuous
@@ -823,13 +867,14 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     const bool need_prior = kernel_prior_terms && (d_grad || d_energies);
     // the prior kernels only need the packed positions: beside the forward kernel, on a side stream
     static const bool fork_env = []() { const char *e = getenv("EHIC_FORK"); return !(e && !strcmp(e, "0")); }();
-    // (not under per-kernel profiling, whose event pairs assume one stream, and not inside the host pipeline,
-    // whose chunks already keep both compute streams busy)
+    // (not under per-kernel profiling, whose event pairs assume one stream; not when the call is one of several
+    // parts already running side by side -- measured: no gain there, and the host pipeline loses 2 %)
     const bool fork = fork_env && need_forward && need_prior && !m->profiling && !m->in_host_pipeline;
-    cudaStream_t side = !fork ? st : (st == m->st_stream2 ? m->st_stream : m->st_stream2);
+    const int lane_id = st == m->st_stream2 ? 1 : 0;
+    cudaStream_t side = fork ? m->st_side[lane_id] : st;
     if (fork) {
-        CU(cudaEventRecord(m->ev_fork, st));
-        CU(cudaStreamWaitEvent(side, m->ev_fork, 0));
+        CU(cudaEventRecord(m->ev_fork_l[lane_id], st));
+        CU(cudaStreamWaitEvent(side, m->ev_fork_l[lane_id], 0));
     }
     if (need_forward) {
         rc = launch_forward(m, R, m->xs[0], d_norm, d_md, lik && d_grad, lik && d_energies, st, d_lammda);
@@ -839,8 +884,8 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
         rc = launch_prior(m, R, kernel_prior_terms, m->xs[0], d_beta, d_grad != nullptr, d_energies != nullptr, side);
         if (rc) return rc;
         if (fork) {
-            CU(cudaEventRecord(m->ev_join, side));
-            CU(cudaStreamWaitEvent(st, m->ev_join, 0));
+            CU(cudaEventRecord(m->ev_join_l[lane_id], side));
+            CU(cudaStreamWaitEvent(st, m->ev_join_l[lane_id], 0));
         }
     }
     if (d_grad) {
