@@ -779,8 +779,20 @@ struct SlotShift {
     double *xs0, *xt0, *wbuf, *tw, *gprior, *bbox, *partC, *partA, *partP, *partK, *Grow, *Pbuf;
     float *tw32;
     int *cell;
+    double *xs1, *xt1, *energies, *kinetic;
+    VerletDev vl;
     SlotShift(ehic_model *m_, int s) : m(m_)
     {
+        xs1 = m->xs[1]; xt1 = m->xt[1]; energies = m->energies; kinetic = m->kinetic; vl = m->vl;
+        {
+            const size_t z = (size_t)s;
+            m->xs[1] += z * m->wss.xs; m->xt[1] += z * m->wss.xt; m->energies += z * 4; m->kinetic += z;
+            if (m->use_verlet) {
+                const size_t sS = z * (size_t)m->dm.S;
+                m->vl.state += sS; m->vl.stale += sS; m->vl.cnt += sS * m->dm.Np;
+                m->vl.idx += sS * (size_t)m->dm.Np * EHIC_VL_CAP; m->vl.xref += z * m->wss.xs;
+            }
+        }
         xs0 = m->xs[0]; xt0 = m->xt[0]; wbuf = m->wbuf; tw = m->tw; gprior = m->gprior; bbox = m->bbox; partC = m->partC;
         partA = m->partA; partP = m->partP; partK = m->partK; Grow = m->Grow; Pbuf = m->Pbuf; tw32 = m->tw32; cell = m->cell_list;
         const auto &w = m->wss;
@@ -797,6 +809,7 @@ struct SlotShift {
     {
         m->xs[0] = xs0; m->xt[0] = xt0; m->wbuf = wbuf; m->tw = tw; m->gprior = gprior; m->bbox = bbox; m->partC = partC;
         m->partA = partA; m->partP = partP; m->partK = partK; m->Grow = Grow; m->Pbuf = Pbuf; m->tw32 = tw32; m->cell_list = cell;
+        m->xs[1] = xs1; m->xt[1] = xt1; m->energies = energies; m->kinetic = kinetic; m->vl = vl;
     }
 };
 
@@ -826,7 +839,8 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     {   // Large batches run as two halves side by side (second half on st_stream2, in its own workspace slots):
         // the CTAs of one half fill the partial last waves of the other's kernels.  Measured at config D:
         // 1128 -> 1141 grad evals/s; four parts: 1134.  Only when a half is still a large launch.
-        static const int split_env = []() { const char *e = getenv("EHIC_SPLIT"); return e ? atoi(e) : -1; }();
+        const char *se = getenv("EHIC_SPLIT");
+        const int split_env = se ? atoi(se) : -1;
         cudaStream_t st0 = (cudaStream_t)stream;
         const bool heavy = (double)m->dm.S * (double)m->dm.M * (R / 2) >= 2e8;
         const int parts = split_env >= 0 ? split_env : (heavy ? 2 : 1);
@@ -989,9 +1003,43 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
 
 }  // extern "C"
 
+static int enqueue_trajectory_part(ehic_model_t *m, int R, int n_steps, double *d_x, double *d_p,
+                                   const double *d_norm, const double *d_lammda, const double *d_beta,
+                                   const double *d_eps, double *d_H, cudaStream_t st);
+
+// Large batches: the two halves of the replicas as two independent chains on two streams (parallel branches of
+// the captured graph), each in its own workspace slots -- the CTAs of one half fill the partial last waves of
+// the other's kernels, as in ehic_evaluate.
 static int enqueue_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double *d_p,
                               const double *d_norm, const double *d_lammda, const double *d_beta,
                               const double *d_eps, double *d_H, cudaStream_t st)
+{
+    const char *se = getenv("EHIC_SPLIT");
+    const int split_env = se ? atoi(se) : -1;
+    const bool heavy = (double)m->dm.S * (double)m->dm.M * (R / 2) >= 2e8;
+    const int parts = split_env >= 0 ? split_env : (heavy ? 2 : 1);
+    if (parts < 2 || R < 4 || m->profiling || st == m->st_stream2)
+        return enqueue_trajectory_part(m, R, n_steps, d_x, d_p, d_norm, d_lammda, d_beta, d_eps, d_H, st);
+    const int h = R / 2;
+    const size_t per = (size_t)m->dm.S * m->dm.N * 3;
+    CU(cudaEventRecord(m->ev_half, st));
+    CU(cudaStreamWaitEvent(m->st_stream2, m->ev_half, 0));
+    int rc = enqueue_trajectory_part(m, h, n_steps, d_x, d_p, d_norm, d_lammda, d_beta, d_eps, d_H, st);
+    if (rc == EHIC_OK) {
+        SlotShift shift(m, h);
+        rc = enqueue_trajectory_part(m, R - h, n_steps, d_x + h * per, d_p + h * per, d_norm + h,
+                                     d_lammda ? d_lammda + h : nullptr, d_beta ? d_beta + h : nullptr, d_eps + h,
+                                     d_H + 4 * (size_t)h, m->st_stream2);
+    }
+    // join even after an error, so that a stream capture in progress can be ended cleanly
+    cudaEventRecord(m->ev_half_done, m->st_stream2);
+    cudaStreamWaitEvent(st, m->ev_half_done, 0);
+    return rc;
+}
+
+static int enqueue_trajectory_part(ehic_model_t *m, int R, int n_steps, double *d_x, double *d_p,
+                                   const double *d_norm, const double *d_lammda, const double *d_beta,
+                                   const double *d_eps, double *d_H, cudaStream_t st)
 {
     int rc = EHIC_OK;
     int prior_terms = EHIC_TERM_ALL & ~EHIC_TERM_LIKELIHOOD;
@@ -1001,8 +1049,10 @@ static int enqueue_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, 
     // The prior kernels (nonbonded lists, backbone, sphere) only need the positions: they run on a side stream
     // beside the forward kernel and join before the backward / gather kernel (parallel branches of the graph).
     static const bool fork_env = []() { const char *e = getenv("EHIC_FORK"); return !(e && !strcmp(e, "0")); }();
-    const bool fork = fork_env && st != m->st_stream2 && !m->profiling;
-    cudaStream_t side = fork ? m->st_stream2 : st;
+    const bool fork = fork_env && !m->profiling;
+    const int lane_id = st == m->st_stream2 ? 1 : 0;         // second half of a split trajectory
+    cudaStream_t side = fork ? m->st_side[lane_id] : st;
+    cudaEvent_t ev_f = m->ev_fork_l[lane_id], ev_j = m->ev_join_l[lane_id];
     int cur = 0;
     for (int s = 0; s <= n_steps; s++) {
         const bool first = (s == 0), last = (s == n_steps);
@@ -1011,8 +1061,8 @@ static int enqueue_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, 
         const bool fuse_nb = m->use_tiles && m->nb_fused && !ends;
         const int kpt = fuse_nb ? (prior_terms & ~EHIC_TERM_NONBONDED) : prior_terms;
         if (fork && kpt) {
-            CU(cudaEventRecord(m->ev_fork, st));
-            CU(cudaStreamWaitEvent(side, m->ev_fork, 0));
+            CU(cudaEventRecord(ev_f, st));
+            CU(cudaStreamWaitEvent(side, ev_f, 0));
         }
         rc = launch_forward(m, R, m->xs[cur], d_norm, nullptr, true, ends, st, d_lammda);
         if (rc) return rc;
@@ -1020,8 +1070,8 @@ static int enqueue_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, 
             rc = launch_prior(m, R, kpt, m->xs[cur], d_beta, true, ends, side, true);
             if (rc) return rc;
             if (fork) {
-                CU(cudaEventRecord(m->ev_join, side));
-                CU(cudaStreamWaitEvent(st, m->ev_join, 0));
+                CU(cudaEventRecord(ev_j, side));
+                CU(cudaStreamWaitEvent(st, ev_j, 0));
             }
         }
         GatherArgs ga{};

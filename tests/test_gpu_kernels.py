@@ -555,6 +555,40 @@ def test_verlet_lists_survive_changing_batch_sizes(monkeypatch):
         np.testing.assert_allclose(a[2], b[2], rtol=1e-11)
 
 
+@pytest.mark.parametrize("path,S,N,density", [("rows", 3, 70, 0.4), ("lanes", 33, 48, 0.4), ("tiles", 4, 160, 1.0)])
+def test_split_batches_equal_single_batches(monkeypatch, path, S, N, density):
+    """large batches are evaluated / integrated as two halves on two streams in their own workspace slots
+    (EHIC_SPLIT, automatic for heavy models): same results as one batch, for evaluations and trajectories"""
+    import torch
+    monkeypatch.setenv("EHIC_PATH", path)
+    monkeypatch.setenv("EHIC_TRAJ", "multi")
+    monkeypatch.setenv("EHIC_TILE_MIN_FILL", "0.2")
+    pb = make_problem(seed=31, S=S, N=N, density=density, step=0.8)
+    R, L = 5, 7
+    rng = np.random.default_rng(2)
+    X = np.stack([pb["X"] + rng.normal(scale=0.05, size=pb["X"].shape) for _ in range(R)]).reshape(R, -1)
+    P = rng.normal(size=X.shape)
+    norm = rng.uniform(2, 4, R); lam = np.linspace(0.2, 1, R); bet = np.linspace(1, 0.3, R); eps = np.full(R, 1e-3)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device=dev)
+    res = {}
+    for split in ("1", "2"):
+        monkeypatch.setenv("EHIC_SPLIT", split)
+        m = _model(pb, False, max_replicas=R)
+        assert m.info()["path"] == path
+        g = torch.zeros(R, X.shape[1], dtype=torch.float64, device=dev); E = torch.zeros(R, 4, dtype=torch.float64, device=dev)
+        md = torch.zeros(R, len(pb["data"]), dtype=torch.float64, device=dev)
+        m.evaluate_device(R, t(X), t(norm), t(lam), t(bet), grad=g, energies=E, md=md)
+        x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            m.hmc_trajectory_device(R, L, x_t, p_t, t(norm), t(lam), t(bet), t(eps), H_t)
+        torch.cuda.synchronize()
+        res[split] = [a.cpu().numpy() for a in (g, E, md, x_t, p_t, H_t)]
+        m.close()
+    for a, b in zip(res["2"], res["1"]):
+        assert np.array_equal(a, b)          # the same kernels on the same data: bit-identical
+
+
 # ---- cell-grid nonbonded path ------------------------------------------------------------------------
 
 def _ball(rng, n, radius):
