@@ -842,7 +842,7 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
         const char *se = getenv("EHIC_SPLIT");
         const int split_env = se ? atoi(se) : -1;
         cudaStream_t st0 = (cudaStream_t)stream;
-        const bool heavy = (double)m->dm.S * (double)m->dm.M * (R / 2) >= 2e8;
+        const bool heavy = m->use_tiles && (double)m->dm.S * (double)m->dm.M * (R / 2) >= 2e8;     // see enqueue_trajectory
         const int parts = split_env >= 0 ? split_env : (heavy ? 2 : 1);
         if (parts >= 2 && R >= 2 * parts && !m->in_host_pipeline && !m->profiling && st0 != m->st_stream2) {
             const size_t per = (size_t)m->dm.S * m->dm.N * 3;
@@ -1016,7 +1016,9 @@ static int enqueue_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, 
 {
     const char *se = getenv("EHIC_SPLIT");
     const int split_env = se ? atoi(se) : -1;
-    const bool heavy = (double)m->dm.S * (double)m->dm.M * (R / 2) >= 2e8;
+    // automatic only on the dense tile path (FP64-bound kernels whose last waves are partial); on the sparse
+    // lane path, bound by L2 traffic, two concurrent halves were measured 5 % slower
+    const bool heavy = m->use_tiles && (double)m->dm.S * (double)m->dm.M * (R / 2) >= 2e8;
     const int parts = split_env >= 0 ? split_env : (heavy ? 2 : 1);
     if (parts < 2 || R < 4 || m->profiling || st == m->st_stream2)
         return enqueue_trajectory_part(m, R, n_steps, d_x, d_p, d_norm, d_lammda, d_beta, d_eps, d_H, st);
