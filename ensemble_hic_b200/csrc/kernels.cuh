@@ -1722,9 +1722,12 @@ backward_tile_kernel(DevModel dm, TileDev td, BackwardTileArgs ba)
 {
     extern __shared__ __align__(16) double smem[];        // [STAGES][2][1024]: dc, w
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // row block outermost, ascending: row block I walks the tiles of columns >= 128 I, so the CTAs with the most
+    // work of ALL replicas start first and the short ones fill the end of the launch (longest-first scheduling)
     const int kg = blockIdx.x % ba.n_kg;
-    const int I = (blockIdx.x / ba.n_kg) % td.n_rb;
-    const int r = blockIdx.x / (ba.n_kg * td.n_rb);
+    const int n_rep = gridDim.x / (ba.n_kg * td.n_rb);
+    const int r = (blockIdx.x / ba.n_kg) % n_rep;
+    const int I = blockIdx.x / (ba.n_kg * n_rep);
     const int k = kg * 4 + warp;
     const bool k_ok = k < dm.S;
     const long long rk = (long long)r * dm.S + (k_ok ? k : dm.S - 1);
@@ -2018,9 +2021,12 @@ backward_tile32_kernel(DevModel dm, TileDev td, BackwardTile32Args ba)
     extern __shared__ __align__(16) double smem[];        // [STAGES][2][1024] floats: dc, w
     float *sf = reinterpret_cast<float *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // row block outermost, ascending: row block I walks the tiles of columns >= 128 I, so the CTAs with the most
+    // work of ALL replicas start first and the short ones fill the end of the launch (longest-first scheduling)
     const int kg = blockIdx.x % ba.n_kg;
-    const int I = (blockIdx.x / ba.n_kg) % td.n_rb;
-    const int r = blockIdx.x / (ba.n_kg * td.n_rb);
+    const int n_rep = gridDim.x / (ba.n_kg * td.n_rb);
+    const int r = (blockIdx.x / ba.n_kg) % n_rep;
+    const int I = blockIdx.x / (ba.n_kg * n_rep);
     const int k = kg * 4 + warp;
     const bool k_ok = k < dm.S;
     const long long rk = (long long)r * dm.S + (k_ok ? k : dm.S - 1);
