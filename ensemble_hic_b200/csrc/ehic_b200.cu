@@ -328,7 +328,20 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
             ld.nkg = nkg;
 #define UPL(vec, field)                                             \
     do { rc = upload(m, vec, &ld.field); if (rc) { ehic_model_destroy(m); return rc; } } while (0)
-            UPL(pairs, pairs); UPL(LL.slot_a, slot_a); UPL(LL.slot_b, slot_b); UPL(roff, row_off); UPL(ents, ent);
+            // backward work items: longest rows first when the rows are ragged (the 4 warps of a CTA then walk rows of
+            // similar length and the short rows fill the end of the launch); natural order otherwise, which keeps
+            // the partner rows that neighbouring beads share (banded lists) close in time
+            std::vector<int32_t> order(N);
+            std::iota(order.begin(), order.end(), 0);
+            {
+                int64_t mx = 0;
+                for (int b = 0; b < N; b++) mx = std::max<int64_t>(mx, L.row_len[b]);
+                const char *lo = getenv("EHIC_LANE_ORDER");
+                const bool ragged = (double)mx * N > 1.5 * 2.0 * (double)L.M;       // max > 1.5 x mean row length
+                if (lo ? !strcmp(lo, "sorted") : ragged)
+                    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return L.row_len[a] > L.row_len[b]; });
+            }
+            UPL(pairs, pairs); UPL(LL.slot_a, slot_a); UPL(LL.slot_b, slot_b); UPL(roff, row_off); UPL(ents, ent); UPL(order, order);
 #undef UPL
             m->use_lanes = true;
             m->n_quads = (N + EHIC_LANE_WARPS - 1) / EHIC_LANE_WARPS;

@@ -1252,6 +1252,7 @@ struct LaneDev {
     const int *slot_a, *slot_b;     // [M]  CSR positions of (i -> j) and (j -> i)
     const long long *row_off;       // [N+1] CSR: both directions of every pair
     const LaneEnt *ent;             // [2M]
+    const int *order;               // [N] bead handled by backward work item q: identity, or longest rows first for ragged lists
 };
 
 __device__ __forceinline__ void reduce8(double (&r)[8], int lane);      // defined with the tile kernels below
@@ -1357,9 +1358,10 @@ backward_lane_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
     const int tmp = blockIdx.x / n_quads;
     const int kg = tmp % ld.nkg;
     const int r = tmp / ld.nkg;
-    const int b = quad * EHIC_LANE_WARPS + warp;
-    const bool bead_ok = b < dm.N;
-    const int bb = bead_ok ? b : dm.N - 1;
+    const int item = quad * EHIC_LANE_WARPS + warp;
+    const bool bead_ok = item < dm.N;
+    const int b = bead_ok ? ld.order[item] : dm.N - 1;
+    const int bb = b;
     const int k = kg * 32 + lane;
     const bool k_ok = k < dm.S;
     const long long gstride = (long long)dm.Np * 96;
