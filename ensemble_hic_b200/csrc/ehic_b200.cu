@@ -378,7 +378,7 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     DA(m->wbuf, Rm * (size_t)dm.wstride);
     DA(m->gprior, Rm * S * (size_t)N * 3);
     DA(m->bbox, Rm * S * (size_t)L.n_slices * 6);
-    DA(m->partC, Rm * S);
+    DA(m->partC, Rm * S * 3);
     {
         const char *nbm = getenv("EHIC_NB");
         m->use_cells = !exact && (N >= 4096 || (nbm && !strcmp(nbm, "cells") && N >= 32)) && !(nbm && !strcmp(nbm, "pairs"));
@@ -415,7 +415,7 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     {
         auto &w = m->wss;
         w.xs = (size_t)S * 3 * dm.Np; w.xt = (size_t)m->nkt * dm.Np * m->kt * 3; w.wbuf = (size_t)dm.wstride;
-        w.gprior = (size_t)S * N * 3; w.bbox = (size_t)S * L.n_slices * 6; w.partC = (size_t)S; w.cell = (size_t)S * N;
+        w.gprior = (size_t)S * N * 3; w.bbox = (size_t)S * L.n_slices * 6; w.partC = (size_t)S * 3; w.cell = (size_t)S * N;
         w.partA = (size_t)std::max(m->nA, 1); w.partP = (size_t)S * m->nPx * 3;
         w.partK = std::max((size_t)L.n_slices * m->nktg * m->gw, (size_t)m->n_quads * EHIC_LANE_WARPS * m->nkt);
     }
@@ -691,7 +691,7 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
     if (verlet) {
         const int vth = std::min(512, std::max(64, (m->dm.N + 31) / 32 * 32));
         verlet_force_kernel<<<(unsigned)((long long)R * m->dm.S), vth, 0, st>>>(m->dm, m->vl, xs, d_beta, gp,
-                                                                                 want_energy ? m->partC : nullptr);
+                                                                                 want_energy ? m->partC : nullptr, terms);
         LAUNCHED();
     }
     if (cells) {

@@ -475,6 +475,73 @@ __device__ __forceinline__ bool structure_fits_cells(const double *__restrict__ 
     return cells <= (double)EHIC_CELL_MAX;      // false for NaN extents
 }
 
+// Backbone and sphere restraints of one bead (IEEE arithmetic and the reference's operation order in both
+// modes); adds to (g0, g1, g2) and accumulates the squared violations.  Shared by prior_kernel and
+// verlet_force_kernel.
+__device__ __forceinline__ void bonded_terms(const DevModel &dm, const double *__restrict__ xk, int Np, int b, bool bead_ok, int bb,
+                                             double xb0, double xb1, double xb2, double rb, int terms,
+                                             double &g0, double &g1, double &g2, double &e_bb, double &e_sp)
+{
+    // backbone: bonds (b-1, b) then (b, b+1), the reference's visiting order (backbone_prior_c.pyx:26-42)
+    if (terms & 4) {
+        const bool has_prev = bead_ok && b > 0 && !isinf(dm.bb_ul[b - 1]);
+        const bool has_next = bead_ok && !isinf(dm.bb_ul[bb]);
+        double res0 = 0.0, res1 = 0.0, res2 = 0.0;
+        if (has_prev) {   // i = b, i-1 = b-1
+            const double ul = dm.bb_ul[b - 1], ll = dm.bb_ll[b - 1];
+            double d0 = __dsub_rn(xb0, xk[b - 1]), d1 = __dsub_rn(xb1, xk[Np + b - 1]), d2 = __dsub_rn(xb2, xk[2 * Np + b - 1]);
+            double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+            if (s > __dmul_rn(ul, ul)) {
+                double d = __dsqrt_rn(s), a = __dsub_rn(d, ul);
+                res0 = __ddiv_rn(__dmul_rn(a, d0), d); res1 = __ddiv_rn(__dmul_rn(a, d1), d); res2 = __ddiv_rn(__dmul_rn(a, d2), d);
+                e_bb += a * a;
+            } else if (s < __dmul_rn(ll, ll)) {
+                double d = __dsqrt_rn(s), a = __dsub_rn(ll, d);
+                res0 = -__ddiv_rn(__dmul_rn(a, d0), d); res1 = -__ddiv_rn(__dmul_rn(a, d1), d); res2 = -__ddiv_rn(__dmul_rn(a, d2), d);
+                e_bb += a * a;
+            }
+        }
+        if (has_next) {   // i = b+1, i-1 = b
+            const double ul = dm.bb_ul[bb], ll = dm.bb_ll[bb];
+            double d0 = __dsub_rn(xk[b + 1], xb0), d1 = __dsub_rn(xk[Np + b + 1], xb1), d2 = __dsub_rn(xk[2 * Np + b + 1], xb2);
+            double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+            if (s > __dmul_rn(ul, ul)) {
+                double d = __dsqrt_rn(s), a = __dsub_rn(d, ul);
+                res0 = __dsub_rn(res0, __ddiv_rn(__dmul_rn(a, d0), d));
+                res1 = __dsub_rn(res1, __ddiv_rn(__dmul_rn(a, d1), d));
+                res2 = __dsub_rn(res2, __ddiv_rn(__dmul_rn(a, d2), d));
+            } else if (s < __dmul_rn(ll, ll)) {
+                double d = __dsqrt_rn(s), a = __dsub_rn(ll, d);
+                res0 = __dadd_rn(res0, __ddiv_rn(__dmul_rn(a, d0), d));
+                res1 = __dadd_rn(res1, __ddiv_rn(__dmul_rn(a, d1), d));
+                res2 = __dadd_rn(res2, __ddiv_rn(__dmul_rn(a, d2), d));
+            }
+        }
+        g0 = __dadd_rn(g0, __dmul_rn(dm.k_bb, res0));
+        g1 = __dadd_rn(g1, __dmul_rn(dm.k_bb, res1));
+        g2 = __dadd_rn(g2, __dmul_rn(dm.k_bb, res2));
+    }
+
+    // sphere (sphere_prior_c.pyx:25-36)
+    if ((terms & 8) && dm.sphere_active) {
+        const double R0 = dm.sph_R;
+        // radius2 + bead_radii2[i] - 2 * radius * bead_radii[i]
+        const double lim = __dsub_rn(__dadd_rn(__dmul_rn(R0, R0), __dmul_rn(rb, rb)), __dmul_rn(__dmul_rn(2.0, R0), rb));
+        double d0 = __dsub_rn(xb0, dm.sph_cx), d1 = __dsub_rn(xb1, dm.sph_cy), d2 = __dsub_rn(xb2, dm.sph_cz);
+        double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+        if (!(s < lim)) {
+            double d = __dsqrt_rn(s);
+            double a = __dsub_rn(__dadd_rn(d, rb), R0);
+            double f = __ddiv_rn(a, d);
+            g0 = __dadd_rn(g0, __dmul_rn(dm.sph_k, __dmul_rn(d0, f)));
+            g1 = __dadd_rn(g1, __dmul_rn(dm.sph_k, __dmul_rn(d1, f)));
+            g2 = __dadd_rn(g2, __dmul_rn(dm.sph_k, __dmul_rn(d2, f)));
+            if (a > 0.0) e_sp += a * a;      // sphere_prior.py:70-72 penalises d + r > R only
+        }
+    }
+
+}
+
 template <bool EXACT, int EHIC_PRIOR_THREADS>
 __global__ void __launch_bounds__(EHIC_PRIOR_THREADS)
 prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restrict__ beta,
@@ -482,8 +549,15 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
              const double *__restrict__ bbox, int cells_enabled, const int *__restrict__ vl_state = nullptr)
 {
     const int k = blockIdx.y, r = blockIdx.z;
-    // HMC trajectories: structures with a usable Verlet list get their nonbonded term from verlet_force_kernel
-    if (vl_state && vl_state[(long long)r * dm.S + k] != 2) terms &= ~2;
+    // HMC trajectories: structures with a usable Verlet list are evaluated by verlet_force_kernel (nonbonded,
+    // backbone and sphere terms in one pass); this kernel keeps those whose list overflowed (state 2)
+    if (vl_state && vl_state[(long long)r * dm.S + k] != 2) {          // CTA-uniform
+        if (partP && threadIdx.x == 0) {
+            double *o = partP + (((long long)r * dm.S + k) * gridDim.x + blockIdx.x) * 3;
+            o[0] = 0.0; o[1] = 0.0; o[2] = 0.0;
+        }
+        return;
+    }
     const int b = blockIdx.x * EHIC_PRIOR_THREADS + threadIdx.x;
     const bool bead_ok = b < dm.N;
     const int bb = bead_ok ? b : dm.N - 1;
@@ -606,64 +680,7 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
         g2 = __dmul_rn(bet, __dmul_rn(k2, a2));
     }
 
-    // backbone: bonds (b-1, b) then (b, b+1), the reference's visiting order (backbone_prior_c.pyx:26-42)
-    if (terms & 4) {
-        const bool has_prev = bead_ok && b > 0 && !isinf(dm.bb_ul[b - 1]);
-        const bool has_next = bead_ok && !isinf(dm.bb_ul[bb]);
-        double res0 = 0.0, res1 = 0.0, res2 = 0.0;
-        if (has_prev) {   // i = b, i-1 = b-1
-            const double ul = dm.bb_ul[b - 1], ll = dm.bb_ll[b - 1];
-            double d0 = __dsub_rn(xb0, xk[b - 1]), d1 = __dsub_rn(xb1, xk[Np + b - 1]), d2 = __dsub_rn(xb2, xk[2 * Np + b - 1]);
-            double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-            if (s > __dmul_rn(ul, ul)) {
-                double d = __dsqrt_rn(s), a = __dsub_rn(d, ul);
-                res0 = __ddiv_rn(__dmul_rn(a, d0), d); res1 = __ddiv_rn(__dmul_rn(a, d1), d); res2 = __ddiv_rn(__dmul_rn(a, d2), d);
-                e_bb += a * a;
-            } else if (s < __dmul_rn(ll, ll)) {
-                double d = __dsqrt_rn(s), a = __dsub_rn(ll, d);
-                res0 = -__ddiv_rn(__dmul_rn(a, d0), d); res1 = -__ddiv_rn(__dmul_rn(a, d1), d); res2 = -__ddiv_rn(__dmul_rn(a, d2), d);
-                e_bb += a * a;
-            }
-        }
-        if (has_next) {   // i = b+1, i-1 = b
-            const double ul = dm.bb_ul[bb], ll = dm.bb_ll[bb];
-            double d0 = __dsub_rn(xk[b + 1], xb0), d1 = __dsub_rn(xk[Np + b + 1], xb1), d2 = __dsub_rn(xk[2 * Np + b + 1], xb2);
-            double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-            if (s > __dmul_rn(ul, ul)) {
-                double d = __dsqrt_rn(s), a = __dsub_rn(d, ul);
-                res0 = __dsub_rn(res0, __ddiv_rn(__dmul_rn(a, d0), d));
-                res1 = __dsub_rn(res1, __ddiv_rn(__dmul_rn(a, d1), d));
-                res2 = __dsub_rn(res2, __ddiv_rn(__dmul_rn(a, d2), d));
-            } else if (s < __dmul_rn(ll, ll)) {
-                double d = __dsqrt_rn(s), a = __dsub_rn(ll, d);
-                res0 = __dadd_rn(res0, __ddiv_rn(__dmul_rn(a, d0), d));
-                res1 = __dadd_rn(res1, __ddiv_rn(__dmul_rn(a, d1), d));
-                res2 = __dadd_rn(res2, __ddiv_rn(__dmul_rn(a, d2), d));
-            }
-        }
-        g0 = __dadd_rn(g0, __dmul_rn(dm.k_bb, res0));
-        g1 = __dadd_rn(g1, __dmul_rn(dm.k_bb, res1));
-        g2 = __dadd_rn(g2, __dmul_rn(dm.k_bb, res2));
-    }
-
-    // sphere (sphere_prior_c.pyx:25-36)
-    if ((terms & 8) && dm.sphere_active) {
-        const double R0 = dm.sph_R;
-        // radius2 + bead_radii2[i] - 2 * radius * bead_radii[i]
-        const double lim = __dsub_rn(__dadd_rn(__dmul_rn(R0, R0), __dmul_rn(rb, rb)), __dmul_rn(__dmul_rn(2.0, R0), rb));
-        double d0 = __dsub_rn(xb0, dm.sph_cx), d1 = __dsub_rn(xb1, dm.sph_cy), d2 = __dsub_rn(xb2, dm.sph_cz);
-        double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-        if (!(s < lim)) {
-            double d = __dsqrt_rn(s);
-            double a = __dsub_rn(__dadd_rn(d, rb), R0);
-            double f = __ddiv_rn(a, d);
-            g0 = __dadd_rn(g0, __dmul_rn(dm.sph_k, __dmul_rn(d0, f)));
-            g1 = __dadd_rn(g1, __dmul_rn(dm.sph_k, __dmul_rn(d1, f)));
-            g2 = __dadd_rn(g2, __dmul_rn(dm.sph_k, __dmul_rn(d2, f)));
-            if (a > 0.0) e_sp += a * a;      // sphere_prior.py:70-72 penalises d + r > R only
-        }
-    }
-
+    bonded_terms(dm, xk, Np, b, bead_ok, bb, xb0, xb1, xb2, rb, terms, g0, g1, g2, e_bb, e_sp);
     if (bead_ok && gprior) {
         const long long at = (((long long)r * dm.S + k) * dm.N + b) * 3;
         gprior[at] = g0; gprior[at + 1] = g1; gprior[at + 2] = g2;
@@ -697,7 +714,7 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
 //   3. thread <-> bead: the 27 surrounding cells are scanned, contacts evaluated with the same
 //      arithmetic as prior_kernel (gather form: each pair seen from both ends, no atomics on FP data).
 // gprior += beta * dE_nb/dx (prior_kernel wrote the backbone / sphere part first);
-// partC[(r*S + k)] = sum a^4 over both visits.
+// partC[(r*S + k)*3] = sum a^4 over both visits (slots +1, +2: backbone / sphere, zero here).
 #define EHIC_CELL_THREADS 256
 
 __global__ void __launch_bounds__(EHIC_CELL_THREADS)
@@ -732,7 +749,7 @@ cell_nonbonded_kernel(DevModel dm, const double *__restrict__ xs, const double *
     }
     __syncthreads();
     if (s_G[0] == 0) {
-        if (partC && tid == 0) partC[rk] = 0.0;
+        if (partC && tid == 0) { partC[rk * 3] = 0.0; partC[rk * 3 + 1] = 0.0; partC[rk * 3 + 2] = 0.0; }
         return;
     }
     const double edge = s_box[6], inv = 1.0 / edge;
@@ -824,7 +841,7 @@ cell_nonbonded_kernel(DevModel dm, const double *__restrict__ xs, const double *
         if (tid == 0) {
             double t = 0.0;
             for (int q = 0; q < EHIC_CELL_THREADS / 32; q++) t += s_red[0][q];
-            partC[rk] = t;
+            partC[rk * 3] = t; partC[rk * 3 + 1] = 0.0; partC[rk * 3 + 2] = 0.0;
         }
     }
 }
@@ -843,8 +860,8 @@ cell_nonbonded_kernel(DevModel dm, const double *__restrict__ xs, const double *
 //                         structure); stale[rk] = list missing or some bead beyond skin / 2
 //   verlet_build_kernel   stale structures only: thread <-> bead, sweep over all partners (slice boxes
 //                         prune as in prior_kernel), list[bead][slot] ascending, x_ref = x
-//   verlet_force_kernel   CTA <-> structure: gprior += beta * 2k * sum (r_i + r_j - d)^3 / d * (x_o - x_b),
-//                         partC[rk] = sum a^4 over both visits
+//   verlet_force_kernel   CTA <-> structure: gprior = beta * 2k * sum (r_i + r_j - d)^3 / d * (x_o - x_b)
+//                         + backbone and sphere terms; partC[rk*3 + {0,1,2}] = energy sums of the three terms
 #define EHIC_VL_CAP 64
 struct VerletDev {
     int *state, *stale;     // [R*S]
@@ -946,19 +963,19 @@ verlet_build_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, do
     if (over) atomicExch(&vl.state[rk], 2);                        // integer flag: same outcome in any order
 }
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 verlet_force_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, const double *__restrict__ beta,
-                    double *__restrict__ gprior, double *__restrict__ partC)
+                    double *__restrict__ gprior, double *__restrict__ partC, int terms)
 {
     const long long rk = blockIdx.x;
     const int r = (int)(rk / dm.S);
-    __shared__ double sh[32];
+    __shared__ double sh[3][32];
     const int nth = blockDim.x;                                    // one pass over the beads when N <= 1024
     __shared__ int s_bin[EHIC_VL_CAP + 2];
     __shared__ short s_perm[EHIC_CELL_MAX];                        // N < EHIC_CELL_MAX on this path
     const int st = vl.state[rk];
     if (st == 2) {                                                 // prior_kernel evaluated this structure
-        if (partC && threadIdx.x == 0) partC[rk] = 0.0;
+        if (partC && threadIdx.x == 0) { partC[rk * 3] = 0.0; partC[rk * 3 + 1] = 0.0; partC[rk * 3 + 2] = 0.0; }
         return;
     }
     const int Np = dm.Np, N = dm.N;
@@ -984,7 +1001,7 @@ verlet_force_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, co
         for (int b = threadIdx.x; b < N; b += nth) s_perm[atomicAdd(&s_bin[EHIC_VL_CAP - cnt[b] + 1], 1)] = (short)b;
         __syncthreads();
     }
-    double e_nb = 0.0;
+    double e_nb = 0.0, e_bb = 0.0, e_sp = 0.0;
     for (int t = threadIdx.x; t < N; t += nth) {
         const int b = sorted ? (int)s_perm[t] : t;
         const double xb0 = xk[b], xb1 = xk[Np + b], xb2 = xk[2 * Np + b];
@@ -1024,20 +1041,23 @@ verlet_force_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, co
                 }
             }
         }
+        // backbone and sphere terms of the same bead: the prior gradient is written once, nothing is read back
+        double g0 = sc * a0, g1 = sc * a1, g2 = sc * a2;
+        bonded_terms(dm, xk, Np, b, true, b, xb0, xb1, xb2, rb, terms, g0, g1, g2, e_bb, e_sp);
         if (gprior) {
             double *o = gprior + (rk * N + b) * 3;
-            o[0] = fma(sc, a0, o[0]); o[1] = fma(sc, a1, o[1]); o[2] = fma(sc, a2, o[2]);
+            o[0] = g0; o[1] = g1; o[2] = g2;
         }
     }
     if (threadIdx.x == 0 && st == 0) vl.state[rk] = 1;             // built in this step without overflow
     if (partC) {
-        e_nb = warp_sum(e_nb);
-        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = e_nb;
+        e_nb = warp_sum(e_nb); e_bb = warp_sum(e_bb); e_sp = warp_sum(e_sp);
+        if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = e_nb; sh[1][threadIdx.x >> 5] = e_bb; sh[2][threadIdx.x >> 5] = e_sp; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int q = 0; q < (nth >> 5); q++) t += sh[q];
-            partC[rk] = t;
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            for (int q = 0; q < (nth >> 5); q++) { t0 += sh[0][q]; t1 += sh[1][q]; t2 += sh[2][q]; }
+            partC[rk * 3] = t0; partC[rk * 3 + 1] = t1; partC[rk * 3 + 2] = t2;
         }
     }
 }
@@ -2223,8 +2243,11 @@ finalize_kernel(DevModel dm, const double *__restrict__ partA, int nA,
         }
     if (partK)
         for (long long q = threadIdx.x; q < nK; q += 256) e3 += partK[(long long)r * nK + q];
-    if (partC)
-        for (int q = threadIdx.x; q < nC; q += 256) e0 += partC[(long long)r * nC + q];
+    if (partC)      // per structure: (nonbonded, backbone, sphere) from the cell-grid / Verlet-list kernels
+        for (int q = threadIdx.x; q < nC; q += 256) {
+            const double *o = partC + ((long long)r * nC + q) * 3;
+            e0 += o[0]; e1 += o[1]; e2 += o[2];
+        }
     sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = e0; sh[2][threadIdx.x] = e1;
     sh[3][threadIdx.x] = e2; sh[4][threadIdx.x] = e3;
     __syncthreads();
