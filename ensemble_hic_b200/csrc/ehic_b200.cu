@@ -659,7 +659,14 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
     // the two kernels take the same per-structure decision from the slice boxes
     const bool cells = m->use_cells && (terms & EHIC_TERM_NONBONDED);
     m->last_prior_used_cells = cells || verlet;          // partC carries part of the nonbonded energy
-    if (terms & EHIC_TERM_NONBONDED) {
+    // Verlet trajectories of small systems (< 1024 beads: few slices, compact structures) do without the slice
+    // boxes -- list rebuilds are rare and the box kernel costs more per step than its pruning saves per rebuild
+    // (nora2012: 0.41 -> 0.37 ms per step); for long chains the pruned rebuild wins (config D: RE sweeps 1.765
+    // with boxes, 1.738 without)
+    static const int vl_boxes = []() { const char *e = getenv("EHIC_VERLET_BOXES"); return e ? atoi(e) : -1; }();
+    const bool no_boxes = verlet && (vl_boxes >= 0 ? vl_boxes == 0 : m->dm.N < 1024);
+    const double *boxes = no_boxes ? nullptr : m->bbox;
+    if ((terms & EHIC_TERM_NONBONDED) && !no_boxes) {
         dim3 gb((unsigned)m->dm.n_slices, (unsigned)((long long)R * m->dm.S));
         bbox_kernel<<<gb, 32, 0, st>>>(xs, m->bbox, m->dm.N, m->dm.Np, m->dm.n_slices);
         LAUNCHED();
@@ -670,16 +677,16 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
         verlet_check_kernel<<<n_struct, 256, 0, st>>>(m->dm, m->vl, xs);
         LAUNCHED();
         switch (m->prior_threads) {
-        case 64: verlet_build_kernel<64><<<grid, 64, 0, st>>>(m->dm, m->vl, xs, m->r_max, m->bbox); break;
-        case 128: verlet_build_kernel<128><<<grid, 128, 0, st>>>(m->dm, m->vl, xs, m->r_max, m->bbox); break;
-        default: verlet_build_kernel<256><<<grid, 256, 0, st>>>(m->dm, m->vl, xs, m->r_max, m->bbox); break;
+        case 64: verlet_build_kernel<64><<<grid, 64, 0, st>>>(m->dm, m->vl, xs, m->r_max, boxes); break;
+        case 128: verlet_build_kernel<128><<<grid, 128, 0, st>>>(m->dm, m->vl, xs, m->r_max, boxes); break;
+        default: verlet_build_kernel<256><<<grid, 256, 0, st>>>(m->dm, m->vl, xs, m->r_max, boxes); break;
         }
         LAUNCHED();
     }
 #define PK(T)                                                                                         \
     do {                                                                                              \
         if (ex) prior_kernel<true, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max, m->bbox, 0);   \
-        else prior_kernel<false, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max, m->bbox, cells ? 1 : 0, vls);     \
+        else prior_kernel<false, T><<<grid, T, 0, st>>>(m->dm, xs, d_beta, gp, pp, terms, m->r_max, boxes, cells ? 1 : 0, vls);     \
     } while (0)
     switch (m->prior_threads) {
     case 64: PK(64); break;

@@ -588,10 +588,16 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
         const double coarse = (rb + r_max) * (rb + r_max);
         // this warp's own slice box, grown by the largest contact range (+ slack for the <= tests)
         const double reach = 2.0 * r_max * (1.0 + 1e-12);
-        const double *bbk = bbox + ((long long)r * dm.S + k) * dm.n_slices * 6;
+        // bbox == NULL (Verlet trajectories: only structures whose list overflowed land here, compact ones):
+        // no slice boxes were computed, nothing is pruned
+        const bool prune = bbox != nullptr;
+        const double *bbk = prune ? bbox + ((long long)r * dm.S + k) * dm.n_slices * 6 : nullptr;
         const int my_sl = min((int)((blockIdx.x * EHIC_PRIOR_THREADS + threadIdx.x) >> 5), dm.n_slices - 1);
-        const double mlo0 = bbk[my_sl * 6] - reach, mlo1 = bbk[my_sl * 6 + 1] - reach, mlo2 = bbk[my_sl * 6 + 2] - reach;
-        const double mhi0 = bbk[my_sl * 6 + 3] + reach, mhi1 = bbk[my_sl * 6 + 4] + reach, mhi2 = bbk[my_sl * 6 + 5] + reach;
+        const double BIG = 1e300;
+        const double mlo0 = prune ? bbk[my_sl * 6] - reach : -BIG, mlo1 = prune ? bbk[my_sl * 6 + 1] - reach : -BIG,
+                     mlo2 = prune ? bbk[my_sl * 6 + 2] - reach : -BIG;
+        const double mhi0 = prune ? bbk[my_sl * 6 + 3] + reach : BIG, mhi1 = prune ? bbk[my_sl * 6 + 4] + reach : BIG,
+                     mhi2 = prune ? bbk[my_sl * 6 + 5] + reach : BIG;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
         for (int t0 = 0; t0 < dm.N; t0 += EHIC_PRIOR_TILE) {
             __syncthreads();
@@ -603,7 +609,7 @@ prior_kernel(DevModel dm, const double *__restrict__ xs, const double *__restric
             }
             for (int q = threadIdx.x; q < (EHIC_PRIOR_TILE / 32) * 6; q += EHIC_PRIOR_THREADS) {
                 const int psl = min(t0 / 32 + q / 6, dm.n_slices - 1);
-                sbox[q / 6][q % 6] = bbk[psl * 6 + q % 6];
+                sbox[q / 6][q % 6] = prune ? bbk[psl * 6 + q % 6] : 0.0;
             }
             __syncthreads();
             const int cnt = min(EHIC_PRIOR_TILE, dm.N - t0);
@@ -916,10 +922,14 @@ verlet_build_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, do
     __shared__ double2 szr[EHIC_PRIOR_TILE];
     __shared__ double sbox[EHIC_PRIOR_TILE / 32][6];
     const double reach = (2.0 * r_max + vl.skin) * (1.0 + 1e-12);
-    const double *bbk = bbox + rk * dm.n_slices * 6;
+    const bool prune = bbox != nullptr;                            // rebuilds are rare: without boxes the sweep is plain all-pairs
+    const double *bbk = prune ? bbox + rk * dm.n_slices * 6 : nullptr;
     const int my_sl = min((int)((blockIdx.x * THREADS + threadIdx.x) >> 5), dm.n_slices - 1);
-    const double mlo0 = bbk[my_sl * 6] - reach, mlo1 = bbk[my_sl * 6 + 1] - reach, mlo2 = bbk[my_sl * 6 + 2] - reach;
-    const double mhi0 = bbk[my_sl * 6 + 3] + reach, mhi1 = bbk[my_sl * 6 + 4] + reach, mhi2 = bbk[my_sl * 6 + 5] + reach;
+    const double BIG = 1e300;
+    const double mlo0 = prune ? bbk[my_sl * 6] - reach : -BIG, mlo1 = prune ? bbk[my_sl * 6 + 1] - reach : -BIG,
+                 mlo2 = prune ? bbk[my_sl * 6 + 2] - reach : -BIG;
+    const double mhi0 = prune ? bbk[my_sl * 6 + 3] + reach : BIG, mhi1 = prune ? bbk[my_sl * 6 + 4] + reach : BIG,
+                 mhi2 = prune ? bbk[my_sl * 6 + 5] + reach : BIG;
     unsigned short *my_idx = vl.idx + (rk * Np + bb) * (long long)EHIC_VL_CAP;
     int n = 0;
     bool over = false;
@@ -933,7 +943,7 @@ verlet_build_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, do
         }
         for (int q = threadIdx.x; q < (EHIC_PRIOR_TILE / 32) * 6; q += THREADS) {
             const int psl = min(t0 / 32 + q / 6, dm.n_slices - 1);
-            sbox[q / 6][q % 6] = bbk[psl * 6 + q % 6];
+            sbox[q / 6][q % 6] = prune ? bbk[psl * 6 + q % 6] : 0.0;
         }
         __syncthreads();
         const int cnt = min(EHIC_PRIOR_TILE, dm.N - t0);
