@@ -397,8 +397,8 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
                         idx_bytes <= ((size_t)8 << 30);
         if (m->use_verlet) {
             const char *sk = getenv("EHIC_VERLET_SKIN");
-            m->vl.skin = (sk ? atof(sk) : 0.5) * m->r_max;
-            if (!(m->vl.skin > 0.0)) m->vl.skin = 0.5 * m->r_max;
+            m->vl.skin = (sk ? atof(sk) : 0.25) * m->r_max;
+            if (!(m->vl.skin > 0.0)) m->vl.skin = 0.25 * m->r_max;
             int *ip = nullptr;
             const size_t n_int = Rm * S * (size_t)(2 + dm.Np + 32) / 32 * 32 + idx_bytes / sizeof(int);
             if (cudaMalloc(&ip, sizeof(int) * n_int) != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_NOMEM, "cudaMalloc failed"); }
