@@ -403,10 +403,13 @@ def run_b200(args):
                 prof = json.load(f)
         tiles = model.info()["path"] == "tiles"
         roofline = {"bound": "fp64", "kernel": "backward_tile_kernel" if tiles else "gather_kernel", "achieved": ach, "peak": fp64_tf, "unit": "TFLOP/s",
-                    "frac": (ach / fp64_tf) if ach else None, "traffic": prof.get("gather_dram_bytes_per_launch"),
+                    "frac": (ach / fp64_tf) if ach else None, "traffic": prof.get("gather_dram_bytes_per_step", prof.get("gather_dram_bytes_per_launch")),
                     "peak_source": "measured here: DFMA issue-rate micro-benchmark (ehic_fma_peak); FP64/FP32 "
                                    "non-tensor peaks are not in MEASURED_PEAKS.json (SURVEY 8d)",
-                    "algorithmic_flop_per_launch": flop_gather, "kernel_ms": kern,
+                    "algorithmic_flop_per_launch": flop_gather, "launches_per_step": prof.get("launches_per_step", 1),
+                    "note": "per step of the whole resident batch: when the batch runs as several part launches, achieved = "
+                            "algorithmic flop of the batch / summed duration of the kernel's launches, traffic = sum over them",
+                    "kernel_ms": kern,
                     "step": {"achieved": flop_step / (ms / args.steps * 1e-3) / 1e12, "peak": fp64_tf,
                              "frac": flop_step / (ms / args.steps * 1e-3) / 1e12 / fp64_tf,
                              "algorithmic_flop_per_step": flop_step},
