@@ -36,7 +36,7 @@ class EhicError(RuntimeError):
 SYMBOLS = ["ehic_version", "ehic_last_error", "ehic_device_count", "ehic_model_create", "ehic_model_destroy",
            "ehic_model_set_param", "ehic_model_get_param", "ehic_model_info", "ehic_mock_data", "ehic_evaluate",
            "ehic_hmc_trajectory", "ehic_select", "ehic_nblist_host", "ehic_mock_data_host", "ehic_evaluate_host",
-           "ehic_layout_debug", "ehic_fma_peak", "ehic_launch_count", "ehic_profile", "ehic_profile_read"]
+           "ehic_layout_debug", "ehic_launch_count", "ehic_profile", "ehic_profile_read"]
 
 _lib = None
 
@@ -69,7 +69,6 @@ def lib():
     L.ehic_layout_debug.argtypes = [C.c_int32, C.c_int64, vp, C.c_int, vp, _i64p, vp]
     L.ehic_profile.argtypes = [vp, C.c_int]
     L.ehic_profile_read.argtypes = [vp, _dp, _i64p]
-    L.ehic_fma_peak.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp]
     _lib = L
     return L
 

@@ -53,15 +53,15 @@ def get(key, factory):
     m = factory()
     _CACHE[key] = m
     while len(_CACHE) > _MAX:
-        _, old = _CACHE.popitem(last=False)
-        old.close()
+        # only the cache's reference is dropped: priors, forward models and their clones may still hold the
+        # evicted model (`_engine`); Model.__del__ frees the device memory when the last holder goes
+        _CACHE.popitem(last=False)
     return m
 
 
 def clear():
-    while _CACHE:
-        _, m = _CACHE.popitem()
-        m.close()
+    """forget every cached model (device memory is released as soon as nothing else refers to them)"""
+    _CACHE.clear()
 
 
 def contact_model(n_structures, n_beads, data_points, contact_distances, alpha, exact=None, device=None,

@@ -55,5 +55,21 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_fma_peak(force=False, verbose=False):
+    """tools/libehic_fma_peak.so: the FMA issue-rate micro-benchmark bench.py uses as the roofline denominator of
+    the FP64 / FP32 pipes (a measurement aid, kept out of the product library)."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tools", "peak", "fma_peak.cu")
+    out = os.path.join(root, "tools", "libehic_fma_peak.so")
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    cmd = [nvcc_path()] + NVCC_FLAGS + [src, "-o", out + ".tmp.%d" % os.getpid()]
+    if verbose:
+        print("[ensemble_hic_b200]", " ".join(cmd))
+    subprocess.check_call(cmd)
+    os.replace(out + ".tmp.%d" % os.getpid(), out)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

@@ -70,6 +70,9 @@ struct ehic_model {
     int *cell_list = nullptr;
     bool use_cells = false;         // fast mode: nonbonded term through the per-structure cell grid
     bool in_host_pipeline = false;  // ehic_evaluate_host is enqueueing chunks on the two compute streams
+    // tuning knobs from the environment, read ONCE when the model is created (never on the hot path):
+    int opt_split = -1;             // EHIC_SPLIT: parts a large device batch is evaluated in (-1 = automatic)
+    bool opt_traj_multi = false;    // EHIC_TRAJ=multi: never use the one-launch trajectory kernels
     bool use_verlet = false;        // HMC trajectories: nonbonded term from Verlet lists reused across leapfrog steps
     VerletDev vl{};
     double *partA = nullptr, *partP = nullptr, *partK = nullptr;
@@ -102,6 +105,14 @@ struct ehic_model {
     // per-replica strides (elements) of the workspace arrays, for evaluating a chunk in replica slots [s, s+n)
     struct WsStrides { size_t xs = 0, xt = 0, wbuf = 0, tw = 0, gprior = 0, bbox = 0, partC = 0, partA = 0, partP = 0,
                        partK = 0, Grow = 0, Pbuf = 0, cell = 0; } wss;
+};
+
+// RAII: marks the model as "enqueueing the parts of a split call" for the duration of a scope (also on the
+// early-return error paths)
+struct PipelineScope {
+    ehic_model *m; bool prev;
+    explicit PipelineScope(ehic_model *m_) : m(m_), prev(m_->in_host_pipeline) { m->in_host_pipeline = true; }
+    ~PipelineScope() { m->in_host_pipeline = prev; }
 };
 
 static void drop_graphs(ehic_model *m)
@@ -222,6 +233,8 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     ehic_model *m = new (std::nothrow) ehic_model();
     if (!m) return fail(EHIC_ERR_NOMEM, "host allocation failed");
     m->device = device; m->flags = desc->flags; m->max_replicas = desc->max_replicas;
+    { const char *e = getenv("EHIC_SPLIT"); m->opt_split = e ? atoi(e) : -1; }
+    { const char *e = getenv("EHIC_TRAJ"); m->opt_traj_multi = e && !strcmp(e, "multi"); }
     const int N = desc->n_beads, S = desc->n_structures;
     const bool exact = (desc->flags & EHIC_FLAG_EXACT) != 0;
     std::string err = build_layout(N, desc->n_data, desc->data_points, desc->contact_distances, exact, m->layout);
@@ -667,7 +680,7 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
     const bool no_boxes = verlet && (vl_boxes >= 0 ? vl_boxes == 0 : m->dm.N < 1024);
     const double *boxes = no_boxes ? nullptr : m->bbox;
     if ((terms & EHIC_TERM_NONBONDED) && !no_boxes) {
-        dim3 gb((unsigned)m->dm.n_slices, (unsigned)((long long)R * m->dm.S));
+        dim3 gb((unsigned)((long long)R * m->dm.S), (unsigned)m->dm.n_slices);
         bbox_kernel<<<gb, 32, 0, st>>>(xs, m->bbox, m->dm.N, m->dm.Np, m->dm.n_slices);
         LAUNCHED();
     }
@@ -743,7 +756,7 @@ static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_
             ba.tile_clean = m->tile_clean; ba.n_kg = (m->dm.S + 3) / 4; ba.nb = ga.nb_fused; ba.r_max = m->r_max;
             ba.bbox = m->bbox;
             if (ga.nb_fused) {
-                dim3 gb((unsigned)m->dm.n_slices, (unsigned)((long long)R * m->dm.S));
+                dim3 gb((unsigned)((long long)R * m->dm.S), (unsigned)m->dm.n_slices);
                 bbox_kernel<<<gb, 32, 0, st>>>(ga.xs_cur, m->bbox, m->dm.N, m->dm.Np, m->dm.n_slices);
                 LAUNCHED();
             }
@@ -859,14 +872,12 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
     {   // Large batches run as two halves side by side (second half on st_stream2, in its own workspace slots):
         // the CTAs of one half fill the partial last waves of the other's kernels.  Measured at config D:
         // 1128 -> 1141 grad evals/s; four parts: 1134.  Only when a half is still a large launch.
-        const char *se = getenv("EHIC_SPLIT");
-        const int split_env = se ? atoi(se) : -1;
         cudaStream_t st0 = (cudaStream_t)stream;
         const bool heavy = m->use_tiles && (double)m->dm.S * (double)m->dm.M * (R / 2) >= 2e8;     // see enqueue_trajectory
-        const int parts = split_env >= 0 ? split_env : (heavy ? 2 : 1);
+        const int parts = m->opt_split >= 0 ? m->opt_split : (heavy ? 2 : 1);
         if (parts >= 2 && R >= 2 * parts && !m->in_host_pipeline && !m->profiling && st0 != m->st_stream2) {
             const size_t per = (size_t)m->dm.S * m->dm.N * 3;
-            m->in_host_pipeline = true;
+            PipelineScope scope(m);
             CU(cudaEventRecord(m->ev_half, st0));
             CU(cudaStreamWaitEvent(m->st_stream2, m->ev_half, 0));
             for (int c = 0; c < parts && rc == EHIC_OK; c++) {
@@ -877,7 +888,6 @@ int ehic_evaluate(ehic_model_t *m, int R, int terms, const double *d_x, const do
                                    d_energies ? d_energies + 4 * (size_t)r0 : nullptr, d_md ? d_md + (size_t)r0 * m->dm.M : nullptr,
                                    (c & 1) ? m->st_stream2 : st0);
             }
-            m->in_host_pipeline = false;
             if (rc) return rc;
             CU(cudaEventRecord(m->ev_half_done, m->st_stream2));
             CU(cudaStreamWaitEvent(st0, m->ev_half_done, 0));
@@ -953,10 +963,9 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
     cudaStream_t st = (cudaStream_t)stream;
     // small systems: the whole trajectory in ONE kernel launch, state resident in shared memory
     {
-        const char *tj = getenv("EHIC_TRAJ");
         const size_t sm = sizeof(double) * ((size_t)m->dm.S * m->dm.N * 3 + (size_t)m->dm.tot + 32);
         const bool fits = sm <= 200 * 1024 && !(m->flags & EHIC_FLAG_EXACT);
-        if (fits && !(tj && !strcmp(tj, "multi")) && !m->profiling) {
+        if (fits && !m->opt_traj_multi && !m->profiling) {
             if (!m->traj_small_ready) {
                 CU(cudaFuncSetAttribute(trajectory_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                 m->traj_small_ready = true;
@@ -1034,12 +1043,10 @@ static int enqueue_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, 
                               const double *d_norm, const double *d_lammda, const double *d_beta,
                               const double *d_eps, double *d_H, cudaStream_t st)
 {
-    const char *se = getenv("EHIC_SPLIT");
-    const int split_env = se ? atoi(se) : -1;
     // automatic only on the dense tile path (FP64-bound kernels whose last waves are partial); on the sparse
     // lane path, bound by L2 traffic, two concurrent halves were measured 5 % slower
     const bool heavy = m->use_tiles && (double)m->dm.S * (double)m->dm.M * (R / 2) >= 2e8;
-    const int parts = split_env >= 0 ? split_env : (heavy ? 2 : 1);
+    const int parts = m->opt_split >= 0 ? m->opt_split : (heavy ? 2 : 1);
     if (parts < 2 || R < 4 || m->profiling || st == m->st_stream2)
         return enqueue_trajectory_part(m, R, n_steps, d_x, d_p, d_norm, d_lammda, d_beta, d_eps, d_H, st);
     const int h = R / 2;
@@ -1068,6 +1075,11 @@ static int enqueue_trajectory_part(ehic_model_t *m, int R, int n_steps, double *
     if (!m->dm.sphere_active) prior_terms &= ~EHIC_TERM_SPHERE;
     rc = launch_pack(m, R, d_x, m->xs[0], m->xt[0], st);
     if (rc) return rc;
+    if (m->use_verlet) {      // structures whose Verlet list overflowed in an earlier trajectory get a new attempt
+        const long long n = (long long)R * m->dm.S;
+        verlet_retry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->vl, n);
+        LAUNCHED();
+    }
     // The prior kernels (nonbonded lists, backbone, sphere) only need the positions: they run on a side stream
     // beside the forward kernel and join before the backward / gather kernel (parallel branches of the graph).
     static const bool fork_env = []() { const char *e = getenv("EHIC_FORK"); return !(e && !strcmp(e, "0")); }();
@@ -1231,12 +1243,11 @@ int ehic_evaluate_host(ehic_model_t *m, int R, int terms, const double *h_x, con
         CU(cudaStreamWaitEvent(st, m->ev_in[c], 0));
         {
             SlotShift shift(m, r0);
-            m->in_host_pipeline = true;
+            PipelineScope scope(m);
             rc = ehic_evaluate(m, r1 - r0, terms, m->st_x + r0 * per, h_norm ? d_norm + r0 : nullptr,
                                h_lammda ? d_lam + r0 : nullptr, h_beta ? d_bet + r0 : nullptr,
                                h_grad ? m->st_g + r0 * per : nullptr, h_energies ? d_E + 4 * (size_t)r0 : nullptr,
                                h_md ? m->st_md + r0 * M : nullptr, st);
-            m->in_host_pipeline = false;
         }
         if (rc) { cudaDeviceSynchronize(); return rc; }
         CU(cudaEventRecord(m->ev_done[c], st));
@@ -1304,44 +1315,6 @@ int ehic_layout_debug(int32_t n_beads, int64_t n_data, const int64_t *data_point
             if (!ok) return fail(EHIC_ERR_INVALID, "internal: lane view inconsistent");
         }
     }
-    return EHIC_OK;
-}
-
-// ---- measurement helpers -----------------------------------------------------------------------
-
-int ehic_fma_peak(int device, int fp64, int iters, double *tflops, double *ms_per_launch)
-{
-    if (!tflops) return fail(EHIC_ERR_INVALID, "null output");
-    int rc = check_device(device);
-    if (rc) return rc;
-    CU(cudaSetDevice(device));
-    int sms = 0;
-    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    const int blocks = sms * 8, threads = 256, inner = 4096;
-    void *buf = nullptr;
-    CU(cudaMalloc(&buf, (size_t)blocks * threads * 8));
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    if (iters < 1) iters = 1;
-    for (int w = 0; w < 2; w++) {
-        if (fp64) fma_peak_kernel<double><<<blocks, threads>>>((double *)buf, inner, 1.0000001, 1e-9);
-        else fma_peak_kernel<float><<<blocks, threads>>>((float *)buf, inner, 1.0000001f, 1e-9f);
-        LAUNCHED();
-    }
-    CU(cudaEventRecord(e0));
-    for (int w = 0; w < iters; w++) {
-        if (fp64) fma_peak_kernel<double><<<blocks, threads>>>((double *)buf, inner, 1.0000001, 1e-9);
-        else fma_peak_kernel<float><<<blocks, threads>>>((float *)buf, inner, 1.0000001f, 1e-9f);
-        LAUNCHED();
-    }
-    CU(cudaEventRecord(e1));
-    CU(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, e0, e1));
-    double flops = 2.0 * 64.0 * inner * (double)blocks * threads * iters;
-    *tflops = flops / (ms * 1e-3) / 1e12;
-    if (ms_per_launch) *ms_per_launch = ms / iters;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
     return EHIC_OK;
 }
 

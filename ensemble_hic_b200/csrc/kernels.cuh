@@ -413,8 +413,8 @@ forward_rec_kernel(DevModel dm, const double *__restrict__ xt, const double *__r
 __global__ void __launch_bounds__(32)
 bbox_kernel(const double *__restrict__ xs, double *__restrict__ bbox, int N, int Np, int n_slices)
 {
-    const long long rk = blockIdx.y;
-    const int sl = blockIdx.x, lane = threadIdx.x;
+    const long long rk = blockIdx.x;              // R*S can exceed the 65535 limit of grid.y: structures on grid.x
+    const int sl = blockIdx.y, lane = threadIdx.x;
     const int b = min(sl * 32 + lane, N - 1);
     const double *xk = xs + rk * 3LL * Np;
     double lo[3], hi[3];
@@ -876,6 +876,15 @@ struct VerletDev {
     double *xref;           // [R*S][3][Np]
     double skin;
 };
+
+// A list overflow (> EHIC_VL_CAP partners: a transient collapse, NaN coordinates) must not exile the structure to
+// the all-pairs sweep for the rest of the model's life: at the start of every trajectory overflowed structures
+// get one new attempt (state 2 -> 0: rebuilt at the first step, back to 2 only if the list overflows again).
+__global__ void verlet_retry_kernel(VerletDev vl, long long n)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n && vl.state[q] == 2) vl.state[q] = 0;
+}
 
 __global__ void __launch_bounds__(256)
 verlet_check_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs)
@@ -2520,22 +2529,6 @@ __global__ void nblist_fill_kernel(const double *__restrict__ x, int N, double c
             w++;
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------
-// FMA issue-rate micro-benchmarks (roofline denominators for the FP64 / FP32 pipes).
-template <typename T>
-__global__ void __launch_bounds__(256) fma_peak_kernel(T *out, int iters, T a, T b)
-{
-    T v0 = (T)threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
-    for (int i = 0; i < iters; i++) {
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            v0 = v0 * a + b; v1 = v1 * a + b; v2 = v2 * a + b; v3 = v3 * a + b;
-            v4 = v4 * a + b; v5 = v5 * a + b; v6 = v6 * a + b; v7 = v7 * a + b;
-        }
-    }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
 }
 
 }  // namespace ehic

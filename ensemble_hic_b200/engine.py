@@ -206,12 +206,5 @@ def nblist_pairs(coords, cutoff, device=0):
     return pairs[:n.value]
 
 
-def fma_peak(fp64=True, iters=20, device=0):
-    L = _lib.lib()
-    t, ms = C.c_double(), C.c_double()
-    _lib.check(L.ehic_fma_peak(int(device), 1 if fp64 else 0, int(iters), C.byref(t), C.byref(ms)))
-    return t.value, ms.value
-
-
 def launch_count():
     return int(_lib.lib().ehic_launch_count())

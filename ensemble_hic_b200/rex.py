@@ -73,6 +73,12 @@ class EngineBackend(object):
     def tensor(self, a):
         return self.torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)
 
+    def upload(self, a):
+        """host -> device without a stream synchronisation: pinned staging + asynchronous copy (the pinned block
+        is recycled by torch's caching host allocator only after the copy has completed)"""
+        t = self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory()
+        return t.to(self.device, non_blocking=True)
+
     def energies(self, x, norm):
         R = x.shape[0]
         E = self.torch.empty(R, 4, dtype=self.torch.float64, device=self.device)
@@ -92,11 +98,12 @@ class EngineBackend(object):
     def mock_sums(self, x):
         """sum_m fwm(x, norm=1)_m per replica (npsamplers.py:110-116)"""
         R = x.shape[0]
-        one = self.torch.ones(R, dtype=self.torch.float64, device=self.device)
-        md = self.torch.empty(R, self.m.M, dtype=self.torch.float64, device=self.device)
+        if getattr(self, "_md", None) is None or self._md.shape[0] != R:
+            self._one = self.torch.ones(R, dtype=self.torch.float64, device=self.device)
+            self._md = self.torch.empty(R, self.m.M, dtype=self.torch.float64, device=self.device)
         with self.torch.cuda.device(self.device):
-            self.m.mock_data_device(R, x, one, md)
-        return md.sum(dim=1)
+            self.m.mock_data_device(R, x, self._one, self._md)
+        return self._md.sum(dim=1)
 
     def select(self, mask, src, dst):
         from .engine import select_device
@@ -107,12 +114,22 @@ class EngineBackend(object):
 class ReplicaExchange(object):
     """The whole simulation loop of run_simulation.py for the slots of this rank.
 
-    backend      EngineBackend (or a test double with the same five methods)
+    backend      EngineBackend (or a test double with the same methods)
     schedule     {'lammda': [T], 'beta': [T]} for the full ladder
     x0, norm0    initial states of the LOCAL slots: [R_local, n_dof], [R_local]
     hmc          dict(timestep, trajectory_length, adaption_limit)
     norm_prior   (shape, rate) of the Gamma prior if norm is sampled, else None
     counts_sum   sum of the contact counts (shape of the conditional Gamma)
+
+    Between two exchange rounds a rank needs nothing from the others and nothing from its own device:
+    the Metropolis test, the step-size adaptation of the temperatures it holds and the conjugate Gamma
+    draw run on the device (the random numbers they consume -- one uniform and one standard Gamma
+    variate per slot, whose shape lammda * sum(counts) + a does not depend on the state -- are drawn on
+    the host ahead of the trajectory and uploaded asynchronously).  The only collective is ONE
+    all-gather per exchange round (reference schedule: every ``swap_interval``-th iteration,
+    scripts/run_simulation.py:64-69) of four doubles per slot: (U_L, U_nb) for the swap decisions plus
+    the slot's current step size and its acceptance count since the last round, which is how the
+    replicated per-temperature bookkeeping (mcmc_stats.txt) stays identical on every rank.
     """
 
     def __init__(self, backend, schedule, x0, norm0, hmc, norm_prior=None, counts_sum=0.0,
@@ -132,7 +149,7 @@ class ReplicaExchange(object):
         self.L = int(hmc["trajectory_length"])
         self.adaption_limit = int(hmc.get("adaption_limit", 0))
         self.up, self.down = float(hmc.get("adaption_uprate", 1.05)), float(hmc.get("adaption_downrate", 0.95))
-        # per-TEMPERATURE quantities (identical on every rank)
+        # per-TEMPERATURE quantities (identical on every rank after every exchange round / sync_stats())
         ts = np.asarray(hmc["timestep"], dtype=np.float64)      # scalar, or one timestep per temperature (continuation)
         self.timestep_T = np.full(self.T, float(ts)) if ts.ndim == 0 else ts.astype(np.float64).copy()
         assert len(self.timestep_T) == self.T
@@ -150,16 +167,34 @@ class ReplicaExchange(object):
         self.n_swap_rounds = 0
         self.step = 0
         self._buffer = {}          # temperature -> [(step, BinfState)]
+        self._win_count = 0        # iterations since the last dump (for the dump_step thinning)
         self.works = []
-        self.last_accept = np.zeros(self.R, dtype=bool)
+        self.n_collectives = 0
+        self._upload = getattr(backend, "upload", backend.tensor)
+        # device-resident per-slot state: persistent tensors (their pointers are part of the trajectory graph's
+        # signature), updated in place
+        z = np.zeros(self.R)
+        self._lam_d, self._bet_d, self._eps_d = backend.tensor(z), backend.tensor(z), backend.tensor(z)
+        self._acc_d = backend.tensor(z)                                   # accepted trajectories since the last sync
+        self._x_work = backend.torch.empty_like(self.x)
+        self._p_work = backend.torch.empty_like(self.x)
+        self.last_accept = None
+        self._push_temps()
 
     # ---- helpers ---------------------------------------------------------------------------------
     def _local_temps(self):
         return self.temp_of_slot[self.lo:self.hi]
 
+    def _push_temps(self):
+        """(lammda, beta, step size) of the temperatures now held by the local slots -> device"""
+        temps = self._local_temps()
+        packed = self._upload(np.stack([self.lam_T[temps], self.bet_T[temps], self.timestep_T[temps]]))
+        self._lam_d.copy_(packed[0]); self._bet_d.copy_(packed[1]); self._eps_d.copy_(packed[2])
+
     def _allgather_rows(self, local, width):
-        """gather [R_local, width] rows of every rank into a [T, width] numpy array"""
+        """gather [R_local, width] rows of every rank into a [T, width] numpy array (synchronises)"""
         torch = self.be.torch if hasattr(self.be, "torch") else None
+        self.n_collectives += 1
         if self.world == 1 or self.dist is None:
             return local.detach().cpu().numpy() if hasattr(local, "detach") else np.asarray(local)
         rmax = int(np.max(np.diff(self.bounds)))
@@ -170,57 +205,62 @@ class ReplicaExchange(object):
         rows = [out[r][:self.bounds[r + 1] - self.bounds[r]] for r in range(self.world)]
         return torch.cat(rows).cpu().numpy()
 
+    def _fold_stats(self, eps_all, acc_all):
+        """per-slot step sizes and acceptance counts since the last sync -> per-temperature tables"""
+        t = self.temp_of_slot
+        self.timestep_T[t] = eps_all
+        self.n_acc_T[t] += acc_all
+        self._acc_d.zero_()
+
+    def sync_stats(self):
+        """bring timestep_T / n_acc_T up to date on every rank (a collective; called by run() when statistics
+        are written or printed and at its end -- exchange rounds do the same as a by-product)"""
+        torch = self.be.torch
+        G = self._allgather_rows(torch.stack([self._eps_d, self._acc_d], 1), 2)
+        self._fold_stats(G[:, 0], G[:, 1])
+
     # ---- one Gibbs sample for every local slot ------------------------------------------------------
     def sample(self):
-        be, temps = self.be, self._local_temps()
-        lam, bet = be.tensor(self.lam_T[temps]), be.tensor(self.bet_T[temps])
-        eps = be.tensor(self.timestep_T[temps])
-        # persistent work buffers: the device pointers are part of the trajectory graph's signature
-        if getattr(self, "_x_work", None) is None:
-            self._x_work = be.torch.empty_like(self.x)
-            self._p_work = be.torch.empty_like(self.x)
-            self._lam_w, self._bet_w, self._eps_w = lam.clone(), bet.clone(), eps.clone()
+        be, torch, temps = self.be, self.be.torch, self._local_temps()
+        # host side: everything random, none of it depends on the device.  Per-slot streams, drawn in the
+        # order momenta, uniform, gamma.
         if self.momenta == "numpy":
-            self._p_work.copy_(be.tensor(np.stack([rs.normal(size=be.n_dof) for rs in self.rng_slot])))
+            self._p_work.copy_(self._upload(np.stack([rs.normal(size=be.n_dof) for rs in self.rng_slot])))
         else:
             self._p_work.normal_()
+        u = np.array([rs.random_sample() for rs in self.rng_slot])
+        self.n_hmc_T += 1
+        adapt = self.n_hmc_T[temps] < self.adaption_limit
+        host = np.zeros((5, self.R))
+        host[0] = np.log(np.maximum(u, 1e-300))
+        host[1] = np.where(adapt, self.up, 1.0); host[2] = np.where(adapt, self.down, 1.0)
+        if self.norm_prior is not None:
+            shape = self.lam_T[temps] * self.counts_sum + self.norm_prior[0]
+            host[3] = [rs.gamma(sh) for rs, sh in zip(self.rng_slot, shape)]
+        d = self._upload(host)
+        # device side: trajectory, Metropolis test, step-size adaptation, conjugate Gamma draw
         x_new, p = self._x_work, self._p_work
         x_new.copy_(self.x)
-        self._lam_w.copy_(lam); self._bet_w.copy_(bet); self._eps_w.copy_(eps)
-        H = be.trajectory(x_new, p, self.norm, self._lam_w, self._bet_w, self._eps_w, self.L)
-        Hh = H.detach().cpu().numpy()
-        dH = (Hh[:, 2] + Hh[:, 3]) - (Hh[:, 0] + Hh[:, 1])
-        u = np.array([rs.random_sample() for rs in self.rng_slot])
-        acc = np.isfinite(dH) & (np.log(np.maximum(u, 1e-300)) < -dH)
-        mask = be.tensor(acc.astype(np.float64)).to(dtype=be.torch.int32)
-        be.select(mask, x_new, self.x)
+        H = be.trajectory(x_new, p, self.norm, self._lam_d, self._bet_d, self._eps_d, self.L)
+        dH = (H[:, 2] + H[:, 3]) - (H[:, 0] + H[:, 1])
+        acc = torch.isfinite(dH) & (d[0] < -dH)
+        be.select(acc.to(dtype=torch.int32), x_new, self.x)
+        self._acc_d += acc.to(dtype=torch.float64)
+        self._eps_d *= torch.where(acc, d[1], d[2])
         self.last_accept = acc
-        # statistics / adaptation follow the temperature; share them with the other ranks
-        stat = np.zeros((self.R, 1)); stat[:, 0] = acc
-        all_acc = self._allgather_rows(be.tensor(stat), 1)[:, 0]
-        for s in range(self.T):
-            t = self.temp_of_slot[s]
-            self.n_hmc_T[t] += 1
-            self.n_acc_T[t] += all_acc[s]
-            if self.n_hmc_T[t] < self.adaption_limit:
-                self.timestep_T[t] *= self.up if all_acc[s] > 0.5 else self.down
-        # conjugate Gamma draw for the scaling factor (npsamplers.py:42-116)
-        if self.norm_prior is not None:
-            sums = be.mock_sums(self.x).detach().cpu().numpy()
-            new = np.empty(self.R)
-            for q in range(self.R):
-                lam_q = self.lam_T[temps[q]]
-                shape = lam_q * self.counts_sum + self.norm_prior[0]
-                rate = lam_q * sums[q] + self.norm_prior[1]
-                v = self.rng_slot[q].gamma(shape) / rate
-                new[q] = v if v != 0.0 else 1e-10
-            self.norm.copy_(be.tensor(new))
+        if self.norm_prior is not None:       # norm = Gamma(shape) / rate (npsamplers.py:42-116)
+            rate = self._lam_d * be.mock_sums(self.x) + self.norm_prior[1]
+            v = d[3] / rate
+            self.norm.copy_(torch.where(v != 0.0, v, torch.full_like(v, 1e-10)))
         return acc
 
     # ---- one exchange round ----------------------------------------------------------------------------
     def exchange(self):
+        torch = self.be.torch
         E = self.be.energies(self.x, self.norm)
-        U = self._allgather_rows(E[:, :2].contiguous(), 2)            # [T slots, (U_L, U_nb)]
+        G = self._allgather_rows(torch.stack([E[:, 0], E[:, 1], self._eps_d, self._acc_d], 1), 4)
+        self._fold_stats(G[:, 2], G[:, 3])
+        U = G[:, :2]                                                  # [T slots, (U_L, U_nb)]
         pairs = swap_pairs(self.T, self.n_swap_rounds)
         uniforms = self.rng_swap.random_sample(len(pairs))
         acc, works = decide_swaps(pairs, self.slot_of_temp, U, self.lam_T, self.bet_T, uniforms)
@@ -231,12 +271,29 @@ class ReplicaExchange(object):
                 a, b = self.slot_of_temp[t0], self.slot_of_temp[t1]
                 self.slot_of_temp[t0], self.slot_of_temp[t1] = b, a
                 self.temp_of_slot[a], self.temp_of_slot[b] = t1, t0
-        self.works.append((self.step, pairs, works, acc))
+        if self.out is not None:
+            self.works.append((self.step, pairs, works, acc))
         self.n_swap_rounds += 1
+        self._push_temps()
         return acc
 
+    def consistency(self):
+        """what must be identical on every rank (replicated bookkeeping): compared by bench.py / tests through
+        all_gather_object"""
+        return dict(temp_of_slot=self.temp_of_slot.tolist(), timestep_T=self.timestep_T.tolist(),
+                    n_acc_T=self.n_acc_T.tolist(), re_acc=self.re_acc.tolist(), re_try=self.re_try.tolist(),
+                    n_swap_rounds=self.n_swap_rounds)
+
     # ---- output -------------------------------------------------------------------------------------------
-    def _record(self):
+    def _record(self, dump_step):
+        """Every iteration (Gibbs sample or exchange round: rexfw is absent from the reference tree, so which of
+        the two it stores is unpinned; analysis_functions.load_sr_samples makes no assumption on the number of
+        states per file) adds the current state to the dump window; a dump keeps every dump_step-th of them.
+        Only those are copied off the device, and none at all without an output folder."""
+        keep = self._win_count % max(int(dump_step), 1) == 0
+        self._win_count += 1
+        if self.out is None or not keep:
+            return
         xs = self.x.detach().cpu().numpy()
         ns = self.norm.detach().cpu().numpy()
         for q, t in enumerate(self._local_temps()):
@@ -245,9 +302,10 @@ class ReplicaExchange(object):
                 v["norm"] = float(ns[q])
             self._buffer.setdefault(int(t), []).append((self.step, BinfState(v)))
 
-    def _dump(self, first, last, dump_step):
-        """samples/samples_replica{t+1}_{first}-{last}.pickle: list of states, thinned by dump_step.
+    def _dump(self, first, last):
+        """samples/samples_replica{t+1}_{first}-{last}.pickle: list of states (already thinned by dump_step).
         Records of temperatures whose home rank is another rank travel there now (I/O, not hot path)."""
+        self._win_count = 0
         if self.out is None:
             self._buffer = {}
             return
@@ -264,7 +322,7 @@ class ReplicaExchange(object):
                         mine.setdefault(t, []).extend(recs)
         for t, recs in mine.items():
             recs.sort(key=lambda r: r[0])
-            states = [s for (st, s) in recs][::max(int(dump_step), 1)]
+            states = [s for (st, s) in recs]
             fn = os.path.join(self.out, "samples", "samples_replica%d_%d-%d.pickle" % (t + 1, first, last))
             with open(fn, "wb") as f:
                 pickle.dump(states, f, protocol=2)
@@ -300,18 +358,25 @@ class ReplicaExchange(object):
         first = offset
         for it in range(offset, offset + int(n_iterations)):
             self.step = it
-            if it % int(swap_interval) == 0 and it > 0:
+            swapped = it % int(swap_interval) == 0 and it > 0
+            if swapped:
                 self.exchange()
             else:
                 self.sample()
-            self._record()
-            if it % int(statistics_update_interval) == 0 and it > 0:
+            self._record(dump_step)
+            # a continued run starts at it == offset > 0: nothing has been sampled yet, nothing is written
+            want_stats = self.out is not None and it % int(statistics_update_interval) == 0 and it > offset
+            want_status = verbose and it % int(status_interval) == 0 and it > offset
+            if (want_stats or want_status) and not swapped:
+                self.sync_stats()
+            if want_stats:
                 self._write_stats()
-            if verbose and self.rank == 0 and it % int(status_interval) == 0 and it > 0:
+            if want_status and self.rank == 0:
                 print(self.status_line(), flush=True)
-            if it % int(dump_interval) == 0 and it > 0:
-                self._dump(first, it, dump_step)
+            if it % int(dump_interval) == 0 and it > offset:
+                self._dump(first, it)
                 first = it
+        self.sync_stats()
         return self
 
 

@@ -19,6 +19,12 @@
  *     x[R][S][N][3], FP64.  Gradients use the same layout.
  *   - A "replica" is one tempered copy of the posterior: (x, norm, lammda, beta).
  *     Every hot-path call is batched over the R replicas resident on this GPU.
+ *   - Threading: a model is NOT re-entrant.  Its workspace, staging buffers, streams and captured
+ *     trajectory graphs belong to one caller at a time: calls on the same ehic_model_t must be
+ *     serialised by the caller (the reference is single-threaded per replica process).
+ *     Different models may be used from different host threads concurrently.
+ *   - Tuning knobs (EHIC_* environment variables) are read when a model is created,
+ *     never on the hot path.
  */
 #ifndef EHIC_B200_H
 #define EHIC_B200_H
@@ -153,6 +159,10 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
 int ehic_select(int R, int64_t n, const int32_t *d_mask, const double *d_src, double *d_dst, void *stream);
 
 /* ---- neighbour list (c/nblist.c:181-303 nblist_update; nblist.py:51-83) -----------------
+ * PARITY SURFACE of the NBList drop-in (one structure per call, O(N^2) membership sweep, allocates
+ * and copies inside the call): it exists so that list membership can be compared bit for bit with
+ * the reference's.  The production nonbonded path never materialises this list -- ehic_evaluate /
+ * ehic_hmc_trajectory use the pruned all-pairs, cell-grid and Verlet-list kernels instead.
  * Half list of one structure: all i<j with |x_i - x_j|^2 <= cutoff^2, dot product
  * associated as mathutils.c:13-15, rows sorted (canonical order).
  * h_pairs[capacity][2]; *n_pairs receives the total count (returned by NBList.update). */
@@ -179,10 +189,7 @@ int ehic_profile(ehic_model_t *m, int enable);
 int ehic_profile_read(ehic_model_t *m, double ms_out[8], int64_t count_out[8]);
 
 /* ---- measurement helpers ---------------------------------------------------------------
- * FP64 / FP32 FMA issue-rate micro-benchmark (the non-tensor pipe peaks are not
- * in MEASURED_PEAKS.json).  Returns achieved TFLOP/s (2 flop per FMA) over `iters` launches. */
-int ehic_fma_peak(int device, int fp64, int iters, double *tflops, double *ms_per_launch);
-/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+ * number of kernels this library has launched in this process (bench.py "gpu_launches") */
 int64_t ehic_launch_count(void);
 
 #ifdef __cplusplus

@@ -79,7 +79,8 @@ def main():
     rex.run(iters, swap_interval=3, status_interval=1000, dump_interval=10, dump_step=2, statistics_update_interval=5)
     res = dict(rank=rank, lo=rex.lo, hi=rex.hi, temp_of_slot=rex.temp_of_slot.tolist(), timestep_T=rex.timestep_T.tolist(),
                n_acc_T=rex.n_acc_T.tolist(), re_acc=rex.re_acc.tolist(), re_try=rex.re_try.tolist(),
-               x=rex.x.numpy().tolist(), norm=rex.norm.numpy().tolist())
+               x=rex.x.numpy().tolist(), norm=rex.norm.numpy().tolist(),
+               n_collectives=rex.n_collectives, n_swap_rounds=rex.n_swap_rounds, consistency=rex.consistency())
     with open(os.path.join(out_dir, "result_rank%d.json" % rank), "w") as f:
         json.dump(res, f)
     if dist is not None:

@@ -328,3 +328,24 @@ def test_stored_sample_loader_and_reweighting_matrix(tmp_path):
     np.testing.assert_allclose(q[1], E.reshape(-1, 2).sum(1))
     q = reevaluation.reweighting_matrix(E, {"beta": [0.5, 1.0]})
     np.testing.assert_allclose(q[1], E.reshape(-1, 2)[:, 1])
+
+
+def test_model_cache_eviction_keeps_models_alive_for_their_holders():
+    """Evicting a model from the cache of the stateless entry points must not destroy it: priors and forward
+    models (and their clones) keep using the engine they were built with."""
+    from ensemble_hic_b200 import _models
+
+    class Dummy(object):
+        closed = False
+
+        def close(self):
+            self.closed = True
+
+    _models.clear()
+    held = [_models.get(("k", q), Dummy) for q in range(_models._MAX + 3)]
+    assert len(_models._CACHE) == _models._MAX
+    assert not any(d.closed for d in held)
+    assert _models.get(("k", _models._MAX + 2), Dummy) is held[-1]          # still cached
+    assert _models.get(("k", 0), Dummy) is not held[0]                        # evicted: rebuilt on demand
+    _models.clear()
+    assert not any(d.closed for d in held)

@@ -38,6 +38,11 @@ def test_two_ranks_reproduce_one_rank(tmp_path):
     for r in two:                                        # replicated bookkeeping is identical everywhere
         for k in ("temp_of_slot", "timestep_T", "n_acc_T", "re_acc", "re_try"):
             assert r[k] == one[k], k
+    # the only collective between the ranks is ONE all-gather per exchange round (it = 3, 6, ..., 30), plus one
+    # per statistics row that does not fall on an exchange round (it = 5, 10, 20, 25) and one when run() returns
+    for r in two + [one]:
+        assert r["n_swap_rounds"] == 10 and r["n_collectives"] == 10 + 4 + 1
+    assert two[0]["consistency"] == two[1]["consistency"] == one["consistency"]
     x2 = np.concatenate([np.array(r["x"]) for r in two]); n2 = np.concatenate([np.array(r["norm"]) for r in two])
     assert np.array_equal(x2, np.array(one["x"])) and np.array_equal(n2, np.array(one["norm"]))
     assert sum(one["re_try"]) > 0 and sorted(one["temp_of_slot"]) == list(range(5))

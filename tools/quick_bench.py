@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from helpers import random_walk
-from ensemble_hic_b200.engine import Model, fma_peak, launch_count
+from ensemble_hic_b200.engine import Model, launch_count
+from fma_peak import fma_peak
 
 def main():
     N = int(os.environ.get("QB_N", 2000)); S = int(os.environ.get("QB_S", 100)); R = int(os.environ.get("QB_R", 2))
