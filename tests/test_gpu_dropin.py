@@ -287,12 +287,21 @@ def test_batch_reevaluation_of_stored_samples(hairpin, tmp_path):
     settings = parse_config_file(cfg)
     p = make_posterior(settings)
     L, P = p.likelihoods["ensemble_contacts"], p.priors["nonbonded_prior"]
+    # the oracle: calculate_DOS's arithmetic (analysis_functions.py:446-468) with the reference's own kernels
+    from oracle.oracle import OraclePosterior, load_ref
+    fwm = L.forward_model
+    N, S = 23, 2
+    op = OraclePosterior(S, np.asarray(fwm.data_points), fwm["contact_distances"].value, 10.0, np.ones(N), 50.0, 1000.0,
+                         [np.zeros(N - 1)], [np.full(N - 1, 2.0)], [0, N], sphere=(10.0, 5.0, np.zeros(3)),
+                         kernels=load_ref(), nonbonded="nbl")
     out = str(tmp_path / "out") + "/"
     for r in range(3):
         samples = reevaluation.load_sr_samples(out + "samples/", r + 1, 61, 20, 20)
         assert len(samples) == 8
         for q, idx in enumerate(sels[r]):
             x = samples[idx]
+            U = op.energies(x.variables["structures"], x.variables["norm"])
+            np.testing.assert_allclose(energies[r, q], [U[0], U[1]], rtol=1e-10)
             ref = [-L.log_prob(**x.variables), -P.log_prob(structures=x.variables["structures"])]
             np.testing.assert_allclose(energies[r, q], ref, rtol=1e-11)
     sched = {"lammda": np.linspace(0, 1, 3), "beta": np.linspace(0.001, 1, 3)}

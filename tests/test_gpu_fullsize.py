@@ -1,6 +1,8 @@
-"""Parity at BASELINE.json's full sizes, where the CPU oracle would take minutes: size-independent
-properties of the posterior evaluated on the GPU (config D: 2000 beads x 100 structures, dense
-list, M = 1 997 001; and a 10 000-bead sparse case of config E's shape, reduced in structures)."""
+"""Parity at BASELINE.json's full sizes (config D: 2000 beads x 100 structures, dense list, M = 1 997 001; and a
+10 000-bead sparse case of config E's shape, reduced in structures): directly against the oracle -- the reference's
+own compiled Cython (oracle/_ref) when it was built, else its bit-identical C restatement -- at N = 2000,
+M = 1 997 001 with S = 25 (and S = 100 when the host has the memory for the reference's 2 x S x M scratch), plus
+size-independent properties of the posterior evaluated on the GPU."""
 import numpy as np
 import pytest
 
@@ -35,6 +37,55 @@ def _model(pb, monkeypatch=None, path=None, exact=False, R=1, fp32=False):
                      exact=exact, max_replicas=R, fp32=fp32)
     finally:
         os.environ.pop("EHIC_PATH", None)
+
+
+def _oracle(pb, S, nonbonded):
+    from oracle.oracle import OraclePosterior, load_ref
+    N = pb["N"]
+    ul = pb["radii"][:-1] + pb["radii"][1:]
+    return OraclePosterior(S, pb["data"], pb["cds"], 10.0, pb["radii"], 500.0, 500.0, [np.zeros(N - 1)], [ul], [0, N],
+                           kernels=load_ref(), nonbonded=nonbonded)
+
+
+def _host_can_hold(n_bytes):
+    try:
+        import psutil
+        return psutil.virtual_memory().available > 2 * n_bytes
+    except Exception:
+        return False
+
+
+@pytest.mark.parametrize("S", [25, 100])
+def test_config_d_against_the_reference_cython(cfg_d, S):
+    """headline configuration, Model.evaluate against the reference's arithmetic on identical inputs
+    (likelihoods_c.pyx:27-75, forward_models_c.pyx:14-32, forcefield_c.pyx:11-59, backbone_prior_c.pyx:11-44):
+    gradient 1e-10 max-norm relative, log-posterior 1e-10, mock data element-wise; the exact mode bit for bit"""
+    from ensemble_hic_b200 import _lib
+    pb = dict(cfg_d, S=S, X=np.ascontiguousarray(cfg_d["X"][:S]))
+    M = len(pb["data"])
+    if S > 25 and not _host_can_hold(2 * S * M * 8):
+        pytest.skip("host memory too small for the reference's 2 x S x M scratch arrays at S = %d" % S)
+    op = _oracle(pb, S, "n2")
+    x, norm, lam, bet = pb["X"].ravel(), 3.0, 0.7, 0.4
+    g_ref = op.gradient(x, norm, lam, bet)
+    md_ref = op.mock_data(x, norm)
+    U = op.energies(x, norm)
+    lp_ref = -lam * U[0] - bet * U[1] - U[2] - U[3]
+    for exact in (False, True):
+        m = _model(pb, exact=exact)
+        assert m.info()["path"] == ("rows" if exact else "tiles")
+        out = m.evaluate(x, norm, lam, bet, energies=True, md=True)
+        assert relerr(out["grad"][0], g_ref) < 1e-10
+        np.testing.assert_allclose(out["md"][0], md_ref, rtol=1e-10, atol=0.0)
+        E = out["energies"][0]
+        lp = -lam * E[0] - bet * E[1] - E[2] - E[3]
+        assert abs(lp - lp_ref) <= 1e-10 * abs(lp_ref)
+        np.testing.assert_allclose(E[:3], U[:3], rtol=1e-10)
+        if exact:          # reference operation order and IEEE sqrt / div: the Cython entry points bit for bit
+            assert np.array_equal(out["md"][0], md_ref)
+            gl = m.evaluate(x, norm, 1.0, 1.0, terms=_lib.TERM_LIKELIHOOD)["grad"][0]
+            assert np.array_equal(gl, op.gradient(x, norm, 1.0, 1.0, terms=("lik",)))
+        m.close()
 
 
 def test_config_d_paths_and_modes_agree(cfg_d):
@@ -143,3 +194,14 @@ def test_config_e_shape_sparse_list(S, path):
     g = a["grad"][0].reshape(S, N, 3)
     assert np.abs(g.sum(1)).max() < 1e-9 * np.abs(g).max() * N ** 0.5
     fast.close(); exact.close()
+    if S == 8:
+        # ... and against the oracle with the reference's production nonbonded path: cell-grid neighbour list +
+        # PROLSQ (c/nblist.c:181-303, c/forcefield.c:8-109, c/prolsq.c:8-38 restated), likelihood through the
+        # reference's Cython
+        op = _oracle(dict(N=N, radii=radii, data=data, cds=cds), S, "nbl")
+        x = X.ravel()
+        assert relerr(a["grad"][0], op.gradient(x, 3.0, 0.7, 0.4)) < 1e-10
+        np.testing.assert_allclose(a["md"][0], op.mock_data(x, 3.0), rtol=1e-10, atol=0.0)
+        U = op.energies(x, 3.0)
+        np.testing.assert_allclose(a["energies"][0][:3], U[:3], rtol=1e-10)
+        assert op.nbl_ff.nbl.n_dropped() == 0
