@@ -35,7 +35,7 @@ class EhicError(RuntimeError):
 #: every symbol include/ehic_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["ehic_version", "ehic_last_error", "ehic_device_count", "ehic_model_create", "ehic_model_destroy",
            "ehic_model_set_param", "ehic_model_get_param", "ehic_model_info", "ehic_mock_data", "ehic_evaluate",
-           "ehic_hmc_trajectory", "ehic_select", "ehic_nblist_host", "ehic_mock_data_host", "ehic_evaluate_host",
+           "ehic_hmc_trajectory", "ehic_trajectory_plan", "ehic_select", "ehic_nblist_host", "ehic_mock_data_host", "ehic_evaluate_host",
            "ehic_layout_debug", "ehic_launch_count", "ehic_profile", "ehic_profile_read"]
 
 _lib = None
@@ -62,6 +62,7 @@ def lib():
     L.ehic_mock_data.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.ehic_evaluate.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ehic_hmc_trajectory.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ehic_trajectory_plan.argtypes = [vp, C.c_int, C.c_int, _i64p]
     L.ehic_select.argtypes = [C.c_int, C.c_int64, vp, vp, vp, vp]
     L.ehic_nblist_host.argtypes = [C.c_int, vp, C.c_double, vp, C.c_int64, _i64p, C.c_int]
     L.ehic_mock_data_host.argtypes = [vp, C.c_int, vp, vp, vp]

@@ -952,6 +952,25 @@ static int enqueue_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, 
                               const double *d_norm, const double *d_lammda, const double *d_beta,
                               const double *d_eps, double *d_H, cudaStream_t st);
 
+// shared memory of the one-CTA-per-replica trajectory kernel: coordinates of all structures + row-slot weights
+static size_t traj_small_smem(const ehic_model *m)
+{
+    return sizeof(double) * ((size_t)m->dm.S * m->dm.N * 3 + (size_t)m->dm.tot + 32);
+}
+static bool traj_small_ok(const ehic_model *m)
+{
+    return traj_small_smem(m) <= 200 * 1024 && !(m->flags & EHIC_FLAG_EXACT) && !m->opt_traj_multi && !m->profiling;
+}
+
+int ehic_trajectory_plan(const ehic_model_t *m, int R, int n_steps, int64_t out[4])
+{
+    if (!m || !out) return fail(EHIC_ERR_INVALID, "null argument");
+    (void)R; (void)n_steps;
+    out[0] = 0; out[1] = 1; out[2] = 0; out[3] = 0;
+    if (traj_small_ok(m)) { out[0] = 1; out[2] = (int64_t)traj_small_smem(m); out[3] = 1; }
+    return EHIC_OK;
+}
+
 int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double *d_p,
                         const double *d_norm, const double *d_lammda, const double *d_beta,
                         const double *d_eps, double *d_H, void *stream)
@@ -963,9 +982,8 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
     cudaStream_t st = (cudaStream_t)stream;
     // small systems: the whole trajectory in ONE kernel launch, state resident in shared memory
     {
-        const size_t sm = sizeof(double) * ((size_t)m->dm.S * m->dm.N * 3 + (size_t)m->dm.tot + 32);
-        const bool fits = sm <= 200 * 1024 && !(m->flags & EHIC_FLAG_EXACT);
-        if (fits && !m->opt_traj_multi && !m->profiling) {
+        const size_t sm = traj_small_smem(m);
+        if (traj_small_ok(m)) {
             if (!m->traj_small_ready) {
                 CU(cudaFuncSetAttribute(trajectory_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                 m->traj_small_ready = true;

@@ -108,6 +108,14 @@ class Model(object):
         return dict(N=out[0], S=out[1], M=out[2], max_replicas=out[3], flags=out[4], slots=out[5],
                     device=out[6], kt=out[7], path=path)
 
+    TRAJECTORY_MODES = ("graph", "one_cta", "cluster")
+
+    def trajectory_plan(self, R=1, n_steps=1):
+        """how hmc_trajectory_device will run: dict(mode, ctas_per_replica, smem_bytes, launches)"""
+        out = (C.c_int64 * 4)()
+        _lib.check(self._L.ehic_trajectory_plan(self._h, int(R), int(n_steps), out))
+        return dict(mode=self.TRAJECTORY_MODES[out[0]], ctas_per_replica=out[1], smem_bytes=out[2], launches=out[3])
+
     # ---- per-kernel timing ------------------------------------------------------------------
     KERNEL_CLASSES = ("pack", "forward", "prior", "gather", "finalize", "other")
 

@@ -155,6 +155,13 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
                         const double *d_norm, const double *d_lammda, const double *d_beta,
                         const double *d_eps, double *d_H, void *stream);
 
+/* How ehic_hmc_trajectory runs a trajectory of this model (north-star kernel 3: "one launch produces one HMC
+ * proposal"): out[0] = 0 multi-kernel step sequence replayed as one CUDA graph, 1 one kernel launch with one CTA
+ * per replica (state in shared memory), 2 one kernel launch with a thread-block cluster per replica (state split
+ * over the cluster's shared memories); out[1] = CTAs per replica; out[2] = dynamic shared memory per CTA in
+ * bytes; out[3] = kernel launches per trajectory (0 = depends on the step sequence). */
+int ehic_trajectory_plan(const ehic_model_t *m, int R, int n_steps, int64_t out[4]);
+
 /* d_dst[r] = d_src[r] for replicas with d_mask[r] != 0 (row length n doubles) */
 int ehic_select(int R, int64_t n, const int32_t *d_mask, const double *d_src, double *d_dst, void *stream);
 
