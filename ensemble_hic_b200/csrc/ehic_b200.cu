@@ -5,6 +5,7 @@
 // compute-capability-10 device every compute call fails with EHIC_ERR_NODEVICE.
 #include "../../include/ehic_b200.h"
 #include "kernels.cuh"
+#include "traj_cluster.cuh"
 #include "layout.hpp"
 
 #include <atomic>
@@ -13,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -73,6 +75,14 @@ struct ehic_model {
     // tuning knobs from the environment, read ONCE when the model is created (never on the hot path):
     int opt_split = -1;             // EHIC_SPLIT: parts a large device batch is evaluated in (-1 = automatic)
     bool opt_traj_multi = false;    // EHIC_TRAJ=multi: never use the one-launch trajectory kernels
+ bool opt_traj_no_small = false; // EHIC_TRAJ=cluster: skip the one-CTA kernel (prefer the cluster kernel)
+    int opt_cluster = -1;           // EHIC_TRAJ_CLUSTER: 0 = never, 2/4/8 = forced cluster size, -1 = automatic
+    // cluster trajectory kernel (traj_cluster.cuh)
+    bool tc_possible = false;       // static eligibility: lane layout uploaded, Verlet buffers present
+    double *tc_pw = nullptr;        // [max_replicas][(S + 7) * N * 3] momenta in kernel order
+    struct TcPlan { bool ok = false; int R = 0, C = 0, Sc = 0, LK = 0, chunk = 0, conc = 0; size_t smem = 0; };
+    std::vector<TcPlan> tc_plans;   // per batch size R
+    bool tc_attr[4] = {false, false, false, false};
     bool use_verlet = false;        // HMC trajectories: nonbonded term from Verlet lists reused across leapfrog steps
     VerletDev vl{};
     double *partA = nullptr, *partP = nullptr, *partK = nullptr;
@@ -234,7 +244,8 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     if (!m) return fail(EHIC_ERR_NOMEM, "host allocation failed");
     m->device = device; m->flags = desc->flags; m->max_replicas = desc->max_replicas;
     { const char *e = getenv("EHIC_SPLIT"); m->opt_split = e ? atoi(e) : -1; }
-    { const char *e = getenv("EHIC_TRAJ"); m->opt_traj_multi = e && !strcmp(e, "multi"); }
+    { const char *e = getenv("EHIC_TRAJ"); m->opt_traj_multi = e && !strcmp(e, "multi"); m->opt_traj_no_small = e && !strcmp(e, "cluster"); }
+    { const char *e = getenv("EHIC_TRAJ_CLUSTER"); m->opt_cluster = e ? atoi(e) : -1; }
     const int N = desc->n_beads, S = desc->n_structures;
     const bool exact = (desc->flags & EHIC_FLAG_EXACT) != 0;
     std::string err = build_layout(N, desc->n_data, desc->data_points, desc->contact_distances, exact, m->layout);
@@ -322,13 +333,17 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     }
     // sparse lists in fast mode take the lane path (lane <-> structure) when the ensemble fills at least
     // 60 % of the lanes of its structure groups; EHIC_PATH=lanes|rows overrides
-    if (!exact && !m->use_tiles && desc->n_data > 0) {
+    if (!exact && desc->n_data > 0) {
         const char *path = getenv("EHIC_PATH");
         const int nkg = (S + 31) / 32;
         bool want = (double)S >= 0.6 * 32.0 * nkg;
         if (path && !strcmp(path, "lanes")) want = true;
         if (path && !strcmp(path, "rows")) want = false;
-        if (want) {
+        if (m->use_tiles) want = false;
+        // the cluster trajectory kernel walks the same CSR / pair views: its weight table (8 M bytes) must fit beside
+        // the coordinates in shared memory, and Verlet lists index beads with 16 bits
+        const bool tc_want = (size_t)desc->n_data * 8 <= 160 * 1024 && N >= 32 && N < EHIC_CELL_MAX && S >= 2 && m->opt_cluster != 0;
+        if (want || tc_want) {
             LaneLayout LL;
             err = build_lanes(L, LL);
             if (!err.empty()) { ehic_model_destroy(m); return fail(EHIC_ERR_INVALID, err); }
@@ -336,6 +351,7 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
             for (int64_t s = 0; s < L.M; s++) { pairs[s].i = L.pi[s]; pairs[s].j = L.pj[s]; pairs[s].dc = L.pdc[s]; }
             std::vector<LaneEnt> ents(LL.ent_j.size());
             for (size_t e = 0; e < ents.size(); e++) { ents[e].dc = LL.ent_dc[e]; ents[e].j = LL.ent_j[e]; ents[e].pad = 0; }
+            for (int64_t s = 0; s < L.M; s++) { ents[LL.slot_a[s]].pad = (int)s; ents[LL.slot_b[s]].pad = (int)s; }   // pair of the entry
             std::vector<long long> roff(LL.row_off.begin(), LL.row_off.end());
             LaneDev &ld = m->ld;
             ld.nkg = nkg;
@@ -356,7 +372,8 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
             }
             UPL(pairs, pairs); UPL(LL.slot_a, slot_a); UPL(LL.slot_b, slot_b); UPL(roff, row_off); UPL(ents, ent); UPL(order, order);
 #undef UPL
-            m->use_lanes = true;
+            m->use_lanes = want;
+            m->tc_possible = tc_want;
             m->n_quads = (N + EHIC_LANE_WARPS - 1) / EHIC_LANE_WARPS;
         }
     }
@@ -959,15 +976,118 @@ static size_t traj_small_smem(const ehic_model *m)
 }
 static bool traj_small_ok(const ehic_model *m)
 {
-    return traj_small_smem(m) <= 200 * 1024 && !(m->flags & EHIC_FLAG_EXACT) && !m->opt_traj_multi && !m->profiling;
+    return traj_small_smem(m) <= 200 * 1024 && !(m->flags & EHIC_FLAG_EXACT) && !m->opt_traj_multi && !m->opt_traj_no_small &&
+           !m->profiling;
 }
 
-int ehic_trajectory_plan(const ehic_model_t *m, int R, int n_steps, int64_t out[4])
+}  // extern "C"
+
+// ---- cluster trajectory kernel: choice of the cluster size ---------------------------------------------------------
+template <int LK>
+static cudaError_t tc_query(ehic_model *m, int C, size_t smem, int *n_clusters)
 {
-    if (!m || !out) return fail(EHIC_ERR_INVALID, "null argument");
-    (void)R; (void)n_steps;
+    const int slot = LK == 4 ? 0 : LK == 8 ? 1 : LK == 16 ? 2 : 3;
+    if (!m->tc_attr[slot]) {
+        cudaError_t e = cudaFuncSetAttribute(trajectory_cluster_kernel<LK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        m->tc_attr[slot] = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(C * 64)); cfg.blockDim = dim3(EHIC_TC_THREADS); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(n_clusters, trajectory_cluster_kernel<LK>, &cfg);
+}
+
+// One cluster of C CTAs per replica, the S structures split Sc = ceil(S / C) per CTA.  C is the feasible size (shared
+// memory: coordinates of Sc structures + weight table + two chunk buffers) with the smallest estimated trajectory
+// time: waves of co-resident clusters x per-CTA work ~ 1 / C, with a small penalty per doubling for the barriers.
+static const ehic_model::TcPlan &plan_cluster(ehic_model *m, int R)
+{
+    for (const auto &p : m->tc_plans) if (p.R == R) return p;
+    ehic_model::TcPlan best; best.R = R;
+    const bool eligible = m->tc_possible && m->use_verlet && !(m->flags & EHIC_FLAG_EXACT) && !m->opt_traj_multi && m->opt_cluster != 0;
+    if (eligible) {
+        const int N = m->dm.N, S = m->dm.S; const long long M = m->dm.M;
+        double best_cost = 1e300;
+        for (int C : {2, 4, 8}) {
+            if (m->opt_cluster > 0 && C != m->opt_cluster) continue;
+            if (C > S) continue;
+            const int Sc = (S + C - 1) / C;
+            if ((C - 1) * Sc >= S || Sc > 32) continue;                       // every CTA holds at least one structure
+            int LK = 4; while (LK < Sc) LK *= 2;
+            const size_t fixed = traj_cluster_smem(N, Sc, M, 0), cap = 227 * 1024;
+            if (fixed + 16 * (size_t)C * 64 > cap) continue;
+            long long chunk = (long long)((cap - fixed) / 16) / C * C;         // two buffers of `chunk` doubles
+            const long long whole = (M + C - 1) / C * C;
+            if (chunk > whole) chunk = whole;
+            const int n_chunks = (int)((M + chunk - 1) / chunk);
+            if (n_chunks > 32) continue;
+            const size_t smem = traj_cluster_smem(N, Sc, M, (int)chunk);
+            int conc = 0;
+            cudaError_t e = LK == 4 ? tc_query<4>(m, C, smem, &conc) : LK == 8 ? tc_query<8>(m, C, smem, &conc)
+                          : LK == 16 ? tc_query<16>(m, C, smem, &conc) : tc_query<32>(m, C, smem, &conc);
+            if (e != cudaSuccess || conc < 1) { cudaGetLastError(); continue; }
+            const int waves = (R + conc - 1) / conc;
+            const double lane_eff = (double)(LK * C) / (double)S;              // idle lanes: LK > Sc, last CTA short
+            const double cost = waves * lane_eff / C * (1.0 + 0.03 * std::log2((double)C) + 0.005 * n_chunks);
+            if (cost < best_cost) {
+                best_cost = cost;
+                best.ok = true; best.C = C; best.Sc = Sc; best.LK = LK; best.chunk = (int)chunk; best.conc = conc; best.smem = smem;
+            }
+        }
+    }
+    if (m->tc_plans.size() >= 16) m->tc_plans.erase(m->tc_plans.begin());
+    m->tc_plans.push_back(best);
+    return m->tc_plans.back();
+}
+
+static int launch_cluster_trajectory(ehic_model *m, const ehic_model::TcPlan &pl, int R, int n_steps, double *d_x, double *d_p,
+                                     const double *d_norm, const double *d_lammda, const double *d_beta,
+                                     const double *d_eps, double *d_H, cudaStream_t st)
+{
+    if (!m->tc_pw) {
+        const size_t n = (size_t)m->max_replicas * (size_t)(m->dm.S + 7) * m->dm.N * 3;
+        CU(cudaMalloc(&m->tc_pw, sizeof(double) * n));
+        m->owned.push_back(m->tc_pw);
+    }
+    TrajClusterArgs ta{};
+    ta.x = d_x; ta.p = d_p; ta.norm = d_norm; ta.lammda = d_lammda; ta.beta = d_beta; ta.eps = d_eps; ta.H = d_H;
+    ta.pw = m->tc_pw; ta.n_steps = n_steps; ta.C = pl.C; ta.Sc = pl.Sc; ta.chunk = pl.chunk;
+    ta.r_max = m->r_max; ta.skin = m->vl.skin;
+    ta.vl_idx = m->vl.idx; ta.vl_cnt = m->vl.cnt; ta.vl_state = m->vl.state;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(R * pl.C)); cfg.blockDim = dim3(EHIC_TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)pl.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    switch (pl.LK) {
+    case 4: CU(cudaLaunchKernelEx(&cfg, trajectory_cluster_kernel<4>, m->dm, m->ld, ta)); break;
+    case 8: CU(cudaLaunchKernelEx(&cfg, trajectory_cluster_kernel<8>, m->dm, m->ld, ta)); break;
+    case 16: CU(cudaLaunchKernelEx(&cfg, trajectory_cluster_kernel<16>, m->dm, m->ld, ta)); break;
+    default: CU(cudaLaunchKernelEx(&cfg, trajectory_cluster_kernel<32>, m->dm, m->ld, ta)); break;
+    }
+    LAUNCHED();
+    return EHIC_OK;
+}
+
+extern "C" {
+
+int ehic_trajectory_plan(const ehic_model_t *cm, int R, int n_steps, int64_t out[4])
+{
+    if (!cm || !out) return fail(EHIC_ERR_INVALID, "null argument");
+    ehic_model *m = const_cast<ehic_model *>(cm);        // the plan cache is not part of the model's logical state
+    int rc = check_call(m, R);
+    if (rc) return rc;
+    (void)n_steps;
     out[0] = 0; out[1] = 1; out[2] = 0; out[3] = 0;
-    if (traj_small_ok(m)) { out[0] = 1; out[2] = (int64_t)traj_small_smem(m); out[3] = 1; }
+    if (traj_small_ok(m)) { out[0] = 1; out[2] = (int64_t)traj_small_smem(m); out[3] = 1; return EHIC_OK; }
+    if (m->profiling) return EHIC_OK;
+    const ehic_model::TcPlan &pl = plan_cluster(m, R);
+    if (pl.ok) { out[0] = 2; out[1] = pl.C; out[2] = (int64_t)pl.smem; out[3] = 1; }
     return EHIC_OK;
 }
 
@@ -1001,6 +1121,11 @@ int ehic_hmc_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, double
             CU(cudaGetLastError());
             return EHIC_OK;
         }
+    }
+    // medium systems: one launch, one thread-block cluster per replica (traj_cluster.cuh)
+    if (!m->profiling) {
+        const ehic_model::TcPlan &pl = plan_cluster(m, R);
+        if (pl.ok) return launch_cluster_trajectory(m, pl, R, n_steps, d_x, d_p, d_norm, d_lammda, d_beta, d_eps, d_H, st);
     }
     static const bool use_graphs = []() { const char *e = getenv("EHIC_GRAPH"); return !(e && !strcmp(e, "0")); }();
     if (!use_graphs || m->profiling)

@@ -480,6 +480,102 @@ def test_one_launch_trajectory_equals_multi_kernel_trajectory(monkeypatch, S, N,
     np.testing.assert_allclose(res["small"][2], res["multi"][2], rtol=1e-11)
 
 
+@pytest.mark.parametrize("S,N,density,sphere,C,skin", [
+    (30, 70, 0.35, False, 2, None), (30, 70, 0.35, False, 4, None), (30, 70, 0.35, True, 8, None),
+    (9, 100, 0.2, True, 4, "0.02"),           # lanes per structure group > structures per CTA; tiny skin: rebuilds inside the launch
+    (5, 64, 0.5, False, 2, None),             # S not divisible: the last CTA holds fewer structures
+    (13, 40, 1.0, False, 8, None)])
+def test_cluster_trajectory_equals_multi_kernel_trajectory_and_oracle(monkeypatch, S, N, density, sphere, C, skin):
+    """medium systems: the whole trajectory in ONE launch, one thread-block cluster per replica, the structures split
+    over the cluster's CTAs and the ensemble sums exchanged through distributed shared memory -- against the
+    kernel-per-phase path and against the oracle's leapfrog (reference kernels)"""
+    import torch
+    from oracle.oracle import OraclePosterior, leapfrog
+    from ensemble_hic_b200.engine import launch_count
+    pb = make_problem(seed=S + N + C, S=S, N=N, density=density, radius=1.0, cd_factor=2.0, min_sep=2, step=1.8)
+    if skin is not None:
+        monkeypatch.setenv("EHIC_VERLET_SKIN", skin)
+    R, L = 3, 12
+    rng = np.random.default_rng(4)
+    X = np.stack([pb["X"] + rng.normal(scale=0.05, size=pb["X"].shape) for _ in range(R)]).reshape(R, -1)
+    P = rng.normal(size=X.shape)
+    norm = np.array([2.5, 3.5, 1.5]); lam = np.array([0.3, 1.0, 0.0]); bet = np.array([0.5, 1.0, 0.01]); eps = np.array([1e-3, 2e-3, 5e-3])
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    sph = (10.0, 5.0, np.zeros(3)) if sphere else None
+    res = {}
+    for mode in ("multi", "cluster"):
+        monkeypatch.setenv("EHIC_TRAJ", mode)
+        monkeypatch.setenv("EHIC_TRAJ_CLUSTER", str(C))
+        m = _model(pb, False, k_nb=50.0, k_bb=1000.0, sphere=sph, max_replicas=R)
+        plan = m.trajectory_plan(R, L)
+        assert plan["mode"] == ("graph" if mode == "multi" else "cluster"), plan
+        if mode == "cluster":
+            assert plan["ctas_per_replica"] == C and plan["smem_bytes"] <= 227 * 1024
+        x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
+        l0 = launch_count()
+        for rep in range(2):                                  # twice: the second call starts from the end point of the first
+            m.hmc_trajectory_device(R, L, x_t, p_t, t(norm), t(lam), t(bet), t(eps), H_t)
+        torch.cuda.synchronize()
+        res[mode] = (x_t.cpu().numpy(), p_t.cpu().numpy(), H_t.cpu().numpy(), launch_count() - l0)
+        if mode == "cluster":                                 # the same model still evaluates through the other entry points
+            g = m.evaluate(X, norm, lam, bet)["grad"]
+            assert np.isfinite(g).all()
+        m.close()
+    assert res["cluster"][3] == 2 and res["multi"][3] > 3 * L
+    assert relerr(res["cluster"][0], res["multi"][0]) < 1e-12
+    assert relerr(res["cluster"][1], res["multi"][1]) < 1e-10
+    np.testing.assert_allclose(res["cluster"][2], res["multi"][2], rtol=1e-11)
+    ul = pb["radii"][:-1] + pb["radii"][1:]
+    op = OraclePosterior(S, pb["data"], pb["cds"], pb["alpha"], pb["radii"], 50.0, 1000.0, [np.zeros(N - 1)], [ul], [0, N],
+                         sphere=sph, nonbonded="n2")
+    r = 1
+    x1, p1 = leapfrog(lambda x: op.gradient(x, norm[r], lam[r], bet[r]), X[r], P[r], eps[r], L)
+    x2, p2 = leapfrog(lambda x: op.gradient(x, norm[r], lam[r], bet[r]), x1, p1, eps[r], L)
+    assert relerr(res["cluster"][0][r], x2) < 1e-11 and relerr(res["cluster"][1][r], p2) < 1e-9
+    E0 = -op.log_prob(x1, norm[r], lam[r], bet[r]); E1 = -op.log_prob(x2, norm[r], lam[r], bet[r])
+    H = res["cluster"][2]
+    assert abs(H[r, 0] - E0) <= 1e-10 * abs(E0) and abs(H[r, 2] - E1) <= 1e-10 * abs(E1)
+    assert abs(H[r, 1] - 0.5 * np.sum(p1 ** 2)) <= 1e-9 * H[r, 1] and abs(H[r, 3] - 0.5 * np.sum(p2 ** 2)) <= 1e-9 * H[r, 3]
+
+
+def test_cluster_trajectory_is_the_automatic_choice_for_the_nora2012_shape():
+    """308 beads x 30 structures, M = 10 145 (config_files/nora2012/30structures_3kb.cfg): 222 KB of coordinates do not fit
+    one SM's shared memory beside the weights; the cluster kernel is picked without any override, for the full ladder
+    on one GPU (302 replicas) and for an eighth of it, and reproduces the multi-kernel trajectory"""
+    import os
+    import torch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nora2012.npz"))
+    from ensemble_hic_b200.engine import Model
+    R, L = 5, 8
+    kw = dict(alpha=float(g["alpha"]), k_nb=float(g["k_nb"]), k_bb=float(g["k_bb"]), max_replicas=302)
+    rng = np.random.default_rng(9)
+    X = np.stack([g["X"] + 0.01 * rng.normal(size=g["X"].shape) for _ in range(R)]).reshape(R, -1)
+    P = rng.normal(size=X.shape)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device=dev)
+    lam = np.linspace(0.2, 1.0, R); eps = np.full(R, 1e-3); nrm = np.full(R, float(g["norm"]))
+    res = {}
+    for mode in ("auto", "multi"):
+        if mode == "multi":
+            os.environ["EHIC_TRAJ"] = "multi"
+        try:
+            m = Model(int(g["S"]), g["radii"], g["data"], g["cds"], **kw)
+        finally:
+            os.environ.pop("EHIC_TRAJ", None)
+        if mode == "auto":
+            for Rq in (302, 38):
+                plan = m.trajectory_plan(Rq, 100)
+                assert plan["mode"] == "cluster" and plan["ctas_per_replica"] in (2, 4, 8) and plan["launches"] == 1, plan
+        x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
+        m.hmc_trajectory_device(R, L, x_t, p_t, t(nrm), t(lam), t(lam), t(eps), H_t)
+        torch.cuda.synchronize()
+        res[mode] = (x_t.cpu().numpy(), p_t.cpu().numpy(), H_t.cpu().numpy())
+        m.close()
+    assert relerr(res["auto"][0], res["multi"][0]) < 1e-12 and relerr(res["auto"][1], res["multi"][1]) < 1e-10
+    np.testing.assert_allclose(res["auto"][2], res["multi"][2], rtol=1e-11)
+
+
 # ---- Verlet lists inside trajectories ---------------------------------------------------------------
 
 @pytest.mark.parametrize("scenario", ["chain", "tiny_skin", "overflow"])
