@@ -47,7 +47,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    path = os.environ.get("EHIC_B200_LIB") or _build.build()      # override: a development build of the same library
     L = C.CDLL(path)
     vp = C.c_void_p
     L.ehic_version.restype = C.c_int

@@ -11,7 +11,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libehic_b200.so")
-SOURCES = ["ehic_b200.cu", "kernels.cuh", "layout.hpp"]
+SOURCES = ["ehic_b200.cu", "kernels.cuh", "layout.hpp", "traj_cluster.cuh"]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "ehic_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
             if not force and not _stale():        # another process built it while we waited
                 return LIB
             tmp = LIB + ".tmp.%d" % os.getpid()
-            cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, "ehic_b200.cu"), "-o", tmp]
+            cmd = [nvcc] + NVCC_FLAGS + os.environ.get("EHIC_NVCC_EXTRA", "").split() + [os.path.join(CSRC, "ehic_b200.cu"), "-o", tmp]
             if verbose:
                 print("[ensemble_hic_b200]", " ".join(cmd))
             subprocess.check_call(cmd, cwd=CSRC)

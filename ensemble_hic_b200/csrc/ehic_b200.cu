@@ -76,7 +76,7 @@ struct ehic_model {
     int opt_split = -1;             // EHIC_SPLIT: parts a large device batch is evaluated in (-1 = automatic)
     bool opt_traj_multi = false;    // EHIC_TRAJ=multi: never use the one-launch trajectory kernels
  bool opt_traj_no_small = false; // EHIC_TRAJ=cluster: skip the one-CTA kernel (prefer the cluster kernel)
-    int opt_cluster = -1;           // EHIC_TRAJ_CLUSTER: 0 = never, 2/4/8 = forced cluster size, -1 = automatic
+    int opt_cluster = -1;           // EHIC_TRAJ_CLUSTER: 2/4/8 = use the cluster kernel with this cluster size; with EHIC_TRAJ=cluster and no size: automatic size
     // cluster trajectory kernel (traj_cluster.cuh)
     bool tc_possible = false;       // static eligibility: lane layout uploaded, Verlet buffers present
     double *tc_pw = nullptr;        // [max_replicas][(S + 7) * N * 3] momenta in kernel order
@@ -342,7 +342,10 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         if (m->use_tiles) want = false;
         // the cluster trajectory kernel walks the same CSR / pair views: its weight table (8 M bytes) must fit beside
         // the coordinates in shared memory, and Verlet lists index beads with 16 bits
-        const bool tc_want = (size_t)desc->n_data * 8 <= 160 * 1024 && N >= 32 && N < EHIC_CELL_MAX && S >= 2 && m->opt_cluster != 0;
+        // Opt-in (EHIC_TRAJ=cluster or EHIC_TRAJ_CLUSTER=2/4/8): on the reference's production shape (nora2012 3 kb) the
+        // captured multi-kernel graph measured faster at every batch size, so it stays the default.
+        const bool tc_want = (size_t)desc->n_data * 8 <= 160 * 1024 && N >= 32 && N < EHIC_CELL_MAX && S >= 2 &&
+                             (m->opt_traj_no_small || m->opt_cluster > 0);
         if (want || tc_want) {
             LaneLayout LL;
             err = build_lanes(L, LL);
@@ -1016,7 +1019,7 @@ static const ehic_model::TcPlan &plan_cluster(ehic_model *m, int R)
             if (m->opt_cluster > 0 && C != m->opt_cluster) continue;
             if (C > S) continue;
             const int Sc = (S + C - 1) / C;
-            if ((C - 1) * Sc >= S || Sc > 32) continue;                       // every CTA holds at least one structure
+            if (Sc > 32) continue;                                            // (S >= C: every CTA holds at least one structure)
             int LK = 4; while (LK < Sc) LK *= 2;
             const size_t fixed = traj_cluster_smem(N, Sc, M, 0), cap = 227 * 1024;
             if (fixed + 16 * (size_t)C * 64 > cap) continue;

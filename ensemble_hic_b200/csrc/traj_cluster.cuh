@@ -33,7 +33,9 @@ namespace ehic {
 
 namespace cg = cooperative_groups;
 
+#ifndef EHIC_TC_THREADS
 #define EHIC_TC_THREADS 512
+#endif
 
 struct TrajClusterArgs {
     double *x, *p;                 // [R][S][N][3] in/out (public layout)
@@ -55,6 +57,23 @@ __device__ __forceinline__ double group_sum(double v)
 #pragma unroll
     for (int o = LK >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Halving butterfly over aligned groups of LK lanes: v[t] is every lane's contribution to column t (LK columns);
+// afterwards v[0] of the lane with index kl inside its group is the group total of column kl.  LK - 1 shuffle-adds
+// instead of LK log2(LK); fixed order (deterministic).
+template <int LK>
+__device__ __forceinline__ void halving_reduce(double (&v)[LK], int lane)
+{
+#pragma unroll
+    for (int h = LK / 2; h > 0; h >>= 1) {
+        const bool hi = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; i++) {
+            const double send = hi ? v[i] : v[i + h], keep = hi ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
 }
 
 __device__ __forceinline__ double block_sum512(double v, double *sh /* [32] */)
@@ -80,9 +99,9 @@ trajectory_cluster_kernel(DevModel dm, LaneDev ld, TrajClusterArgs ta)
     const int r = blockIdx.x / C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = dm.N, S = dm.S, Np = dm.Np, Sc = ta.Sc, M = (int)dm.M;
-    const int k0 = crank * Sc;                         // first structure of this CTA
-    const int nloc = min(Sc, S - k0);                  // structures held here (>= 1, guaranteed by the host)
-    const int rec = Sc * 3;                            // doubles per bead record
+    const int k0 = crank * (S / C) + min(crank, S % C);      // balanced split: the first S % C CTAs hold one structure more
+    const int nloc = S / C + (crank < S % C ? 1 : 0);        // structures held here (>= 1: the host requires S >= C)
+    const int rec = Sc * 3;                            // doubles per bead record (Sc = ceil(S / C))
     const int ndof = N * rec;
     extern __shared__ __align__(16) double smem[];
     double *sx = smem;                                 // [N][Sc][3]
@@ -92,7 +111,11 @@ trajectory_cluster_kernel(DevModel dm, LaneDev ld, TrajClusterArgs ta)
     double *red2 = red + 32;                           // [8][5] cluster reduction of the energy terms (used on rank 0)
     double *s_moved = red2 + 40;                       // [32] per local structure: bound on the displacement since the list build
     unsigned long long *s_maxp = reinterpret_cast<unsigned long long *>(s_moved + 32);   // [32] max |p|^2 of the step (bit pattern)
-    int *s_int = reinterpret_cast<int *>(s_maxp + 32); // [0] bead counter, [1] number of stale structures, [2..33] stale list
+    double *s_rad = reinterpret_cast<double *>(s_maxp + 32);   // [N] bead radii
+    double *s_ul = s_rad + N, *s_ll = s_ul + N;        // [N] bond limits of bond (b, b+1)
+    int *s_int = reinterpret_cast<int *>(s_ll + N);    // [0] bead counter, [1] number of stale structures, [2..33] stale list
+    int *s_off = s_int + 40;                           // [N+1] CSR row offsets
+    int *s_ord = s_off + N + 1;                        // [N] bead handled by work item q (longest rows first)
     const double nrm = ta.norm[r];
     const double lam = ta.lammda ? ta.lammda[r] : 1.0, bet = ta.beta ? ta.beta[r] : 1.0;
     const double eps = ta.eps[r];
@@ -111,6 +134,11 @@ trajectory_cluster_kernel(DevModel dm, LaneDev ld, TrajClusterArgs ta)
         if (k < nloc) { const long long g = ((long long)(k0 + k) * N + b) * 3 + c; xv = gx[g]; pv = gp[g]; }
         sx[q] = xv; pw[q] = pv;
     }
+    for (int q = tid; q < N; q += EHIC_TC_THREADS) {
+        s_rad[q] = dm.radii[q]; s_ul[q] = dm.bb_ul[q]; s_ll[q] = dm.bb_ll[q];
+        s_off[q] = (int)ld.row_off[q]; s_ord[q] = ld.order[q];
+    }
+    if (tid == 0) s_off[N] = (int)ld.row_off[N];
     if (tid < 32) { s_moved[tid] = 0.0; s_maxp[tid] = 0ull; s_int[2 + tid] = tid; }
     if (tid == 0) { s_int[0] = 0; s_int[1] = nloc; }                // first step: every list is built
     __syncthreads();
@@ -122,14 +150,14 @@ trajectory_cluster_kernel(DevModel dm, LaneDev ld, TrajClusterArgs ta)
         for (int item = tid; item < n_stale * N; item += EHIC_TC_THREADS) {
             const int k = s_int[2 + item / N], b = item % N;
             const double *xb = sx + (b * Sc + k) * 3;
-            const double xb0 = xb[0], xb1 = xb[1], xb2 = xb[2], rb = dm.radii[b];
+            const double xb0 = xb[0], xb1 = xb[1], xb2 = xb[2], rb = s_rad[b];
             unsigned short *row = ta.vl_idx + ((rS + k0 + k) * Np + b) * (long long)EHIC_VL_CAP;
             int n = 0;
             for (int o = 0; o < N; o++) {
                 const double *xo = sx + (o * Sc + k) * 3;
                 const double dx = xo[0] - xb0, dy = xo[1] - xb1, dz = xo[2] - xb2;
                 const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                const double lim = rb + dm.radii[o] + skin;
+                const double lim = rb + s_rad[o] + skin;
                 if (!(s2 >= lim * lim) && o != b) {              // !(>=): NaN distances are listed
                     if (n < EHIC_VL_CAP) row[n] = (unsigned short)o;
                     n++;
@@ -153,35 +181,40 @@ trajectory_cluster_kernel(DevModel dm, LaneDev ld, TrajClusterArgs ta)
         for (int q = 0; q < n_chunks; q++) {
             const int m_base = q * ta.chunk, m_end = min(m_base + ta.chunk, M);
             double *bufA = sA + (q & 1) * ta.chunk;
-            const int n_groups = (m_end - m_base + PW - 1) / PW;
-            for (int g0 = warp; g0 < n_groups; g0 += 2 * NW) {
-                // two groups of PW pairs in flight (independent dependency chains)
-                int mA = m_base + g0 * PW + slot, mB = m_base + (g0 + NW) * PW + slot;
-                const bool vA = mA < m_end, vB = (g0 + NW < n_groups) && mB < m_end;
-                mA = vA ? mA : m_end - 1; mB = vB ? mB : m_end - 1;
-                const int4 pa = __ldg(reinterpret_cast<const int4 *>(ld.pairs + mA));
-                const int4 pb = __ldg(reinterpret_cast<const int4 *>(ld.pairs + mB));
-                const double *ai = sx + (pa.x * Sc + kq) * 3, *aj = sx + (pa.y * Sc + kq) * 3;
-                const double *bi = sx + (pb.x * Sc + kq) * 3, *bj = sx + (pb.y * Sc + kq) * 3;
-                const double adx = ai[0] - aj[0], ady = ai[1] - aj[1], adz = ai[2] - aj[2];
-                const double bdx = bi[0] - bj[0], bdy = bi[1] - bj[1], bdz = bi[2] - bj[2];
-                const double as2 = fma(adz, adz, fma(ady, ady, adx * adx));
-                const double bs2 = fma(bdz, bdz, fma(bdy, bdy, bdx * bdx));
-                const double ard = rsqrt_nr(as2), brd = rsqrt_nr(bs2);
-                const double att = alpha * (__hiloint2double(pa.w, pa.z) - as2 * ard);
-                const double btt = alpha * (__hiloint2double(pb.w, pb.z) - bs2 * brd);
-                const double arq = rsqrt_nr(fma(att, att, 1.0)), brq = rsqrt_nr(fma(btt, btt, 1.0));
-                double sa = kv ? fma(att, arq, 1.0) : 0.0, sb = kv ? fma(btt, brq, 1.0) : 0.0;
-                sa = group_sum<LK>(sa); sb = group_sum<LK>(sb);
-                if (kl == 0) {
-                    if (vA) {
-                        const int rel = mA - m_base, owner = rel / sub;
-                        cluster.map_shared_rank(bufA, owner)[crank * sub + (rel - owner * sub)] = sa;
-                    }
-                    if (vB) {
-                        const int rel = mB - m_base, owner = rel / sub;
-                        cluster.map_shared_rank(bufA, owner)[crank * sub + (rel - owner * sub)] = sb;
-                    }
+            // blocks of 32 consecutive pairs: ONE coalesced load brings the block's (i, j, dc) records, one per lane
+            // (the next block's is requested before this one is worked on); the records are then handed to the LK
+            // lanes of a pair by shuffles, LK steps of PW pairs each; the per-lane terms of the LK steps are reduced
+            // over the structures with one halving butterfly, after which every lane holds the sum of ONE pair
+            const int n_blocks = (m_end - m_base + 31) / 32;
+            int4 nxt = make_int4(0, 0, 0, 0);
+            if (warp < n_blocks) nxt = __ldg(reinterpret_cast<const int4 *>(ld.pairs + min(m_base + 32 * warp + lane, m_end - 1)));
+            for (int blk = warp; blk < n_blocks; blk += NW) {
+                const int4 cur = nxt;
+                const int m_b = m_base + 32 * blk;
+                if (blk + NW < n_blocks) nxt = __ldg(reinterpret_cast<const int4 *>(ld.pairs + min(m_b + 32 * NW + lane, m_end - 1)));
+                constexpr int NV = LK <= 16 ? LK : 1;          // LK = 32: the terms are reduced one step at a time
+                double v[NV];
+                double tot = 0.0;
+#pragma unroll
+                for (int t = 0; t < LK; t++) {
+                    const int src = t * PW + slot;
+                    const int pi = __shfl_sync(0xffffffffu, cur.x, src), pj = __shfl_sync(0xffffffffu, cur.y, src);
+                    const double dc = __hiloint2double(__shfl_sync(0xffffffffu, cur.w, src), __shfl_sync(0xffffffffu, cur.z, src));
+                    const double *ai = sx + (pi * Sc + kq) * 3, *aj = sx + (pj * Sc + kq) * 3;
+                    const double dx = ai[0] - aj[0], dy = ai[1] - aj[1], dz = ai[2] - aj[2];
+                    const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    const double rd = rsqrt_nr(s2);
+                    const double tt = alpha * (dc - s2 * rd);
+                    const double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                    const double term = kv ? fma(tt, rq, 1.0) : 0.0;
+                    if constexpr (LK <= 16) v[t] = term;
+                    else { const double sum = group_sum<LK>(term); tot = (t == kl) ? sum : tot; }
+                }
+                if constexpr (LK <= 16) { halving_reduce<NV>(v, lane); tot = v[0]; }
+                const int m = m_b + kl * PW + slot;           // the pair whose ensemble sum (over this CTA's structures) this lane holds
+                if (m < m_end) {
+                    const int rel = m - m_base, owner = rel / sub;
+                    cluster.map_shared_rank(bufA, owner)[crank * sub + (rel - owner * sub)] = tot;
                 }
             }
             cluster.sync();                              // the partials of chunk q have arrived at their owners
@@ -213,54 +246,77 @@ trajectory_cluster_kernel(DevModel dm, LaneDev ld, TrajClusterArgs ta)
             if (lane == 0) it = atomicAdd(&s_int[0], 1);
             it = __shfl_sync(0xffffffffu, it, 0);
             if (it >= N) break;
-            const int b = ld.order[it];
+            const int b = s_ord[it];
             const double *xbp = sx + (b * Sc + kq) * 3;
             const double xb0 = xbp[0], xb1 = xbp[1], xb2 = xbp[2];
+            const double rb = s_rad[b];
+            // Verlet list of (structure kl, bead b): requested now, consumed after the contact row
+            const long long vat = (rS + k0 + kq) * Np + b;
+            const int vcnt = kv ? ta.vl_cnt[vat] : 0;
+            const unsigned short *vrow = ta.vl_idx + vat * (long long)EHIC_VL_CAP;
+            const uint4 vfirst = *reinterpret_cast<const uint4 *>(vrow + 8 * slot);      // entries [8 slot, 8 slot + 8)
             double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-            {   // contact row of bead b (both directions of every pair are in the CSR view); weights carry lammda
-                const int e0 = (int)ld.row_off[b], e1 = (int)ld.row_off[b + 1];
-                for (int e = e0 + slot; e < e1; e += 2 * PW) {
-                    const int eB = e + PW;
-                    const bool vB = eB < e1;
-                    const int4 va = __ldg(reinterpret_cast<const int4 *>(ld.ent + e));
-                    const int4 vb = __ldg(reinterpret_cast<const int4 *>(ld.ent + (vB ? eB : e)));
-                    const double wa = sW[va.w], wb = vB ? sW[vb.w] : 0.0;
-                    const double *xa = sx + (va.z * Sc + kq) * 3, *xc = sx + (vb.z * Sc + kq) * 3;
-                    const double adx = xa[0] - xb0, ady = xa[1] - xb1, adz = xa[2] - xb2;
-                    const double bdx = xc[0] - xb0, bdy = xc[1] - xb1, bdz = xc[2] - xb2;
-                    const double as2 = fma(adz, adz, fma(ady, ady, adx * adx));
-                    const double bs2 = fma(bdz, bdz, fma(bdy, bdy, bdx * bdx));
-                    const double ard = rsqrt_nr(as2), brd = rsqrt_nr(bs2);
-                    const double att = alpha * (__hiloint2double(va.y, va.x) - as2 * ard);
-                    const double btt = alpha * (__hiloint2double(vb.y, vb.x) - bs2 * brd);
-                    const double arq = rsqrt_nr(fma(att, att, 1.0)), brq = rsqrt_nr(fma(btt, btt, 1.0));
-                    const double fa = wa * ((arq * arq) * (arq * ard)), fb = wb * ((brq * brq) * (brq * brd));
-                    g0 = fma(fa, adx, g0); g1 = fma(fa, ady, g1); g2 = fma(fa, adz, g2);
-                    g0 = fma(fb, bdx, g0); g1 = fma(fb, bdy, g1); g2 = fma(fb, bdz, g2);
+            {   // contact row of bead b (both directions of every pair are in the CSR view); weights carry lammda.
+                // Blocks of 32 entries: one coalesced load (entry + its weight per lane), next block requested ahead,
+                // entries handed to the LK lanes of a row slot by shuffles, two steps in flight.
+                const int e0 = s_off[b], e1 = s_off[b + 1];
+                const int n_blocks = (e1 - e0 + 31) / 32;
+                int4 nxt = make_int4(0, 0, 0, 0);
+                if (n_blocks > 0) nxt = __ldg(reinterpret_cast<const int4 *>(ld.ent + min(e0 + lane, e1 - 1)));
+                for (int blk = 0; blk < n_blocks; blk++) {
+                    const int4 cur = nxt;
+                    const int e_b = e0 + 32 * blk;
+                    if (blk + 1 < n_blocks) nxt = __ldg(reinterpret_cast<const int4 *>(ld.ent + min(e_b + 32 + lane, e1 - 1)));
+                    const double wl = (e_b + lane < e1) ? sW[cur.w] : 0.0;      // entries past the end of the row: weight 0
+                    const int n_steps = min(LK, (e1 - e_b + PW - 1) / PW);
+                    for (int t = 0; t < n_steps; t += 2) {
+                        const int sa = t * PW + slot, sb = min(sa + PW, 31);
+                        const bool vb = t + 1 < n_steps;
+                        const int ja = __shfl_sync(0xffffffffu, cur.z, sa), jb = __shfl_sync(0xffffffffu, cur.z, sb);
+                        const double dca = __hiloint2double(__shfl_sync(0xffffffffu, cur.y, sa), __shfl_sync(0xffffffffu, cur.x, sa));
+                        const double dcb = __hiloint2double(__shfl_sync(0xffffffffu, cur.y, sb), __shfl_sync(0xffffffffu, cur.x, sb));
+                        const double wa = __shfl_sync(0xffffffffu, wl, sa);
+                        double wb = __shfl_sync(0xffffffffu, wl, sb);
+                        wb = vb ? wb : 0.0;
+                        const double *xa = sx + (ja * Sc + kq) * 3, *xc = sx + (jb * Sc + kq) * 3;
+                        const double adx = xa[0] - xb0, ady = xa[1] - xb1, adz = xa[2] - xb2;
+                        const double bdx = xc[0] - xb0, bdy = xc[1] - xb1, bdz = xc[2] - xb2;
+                        const double as2 = fma(adz, adz, fma(ady, ady, adx * adx));
+                        const double bs2 = fma(bdz, bdz, fma(bdy, bdy, bdx * bdx));
+                        const double ard = rsqrt_nr(as2), brd = rsqrt_nr(bs2);
+                        const double att = alpha * (dca - as2 * ard), btt = alpha * (dcb - bs2 * brd);
+                        const double arq = rsqrt_nr(fma(att, att, 1.0)), brq = rsqrt_nr(fma(btt, btt, 1.0));
+                        const double fa = wa * ((arq * arq) * (arq * ard)), fb = wb * ((brq * brq) * (brq * brd));
+                        g0 = fma(fa, adx, g0); g1 = fma(fa, ady, g1); g2 = fma(fa, adz, g2);
+                        g0 = fma(fb, bdx, g0); g1 = fma(fb, bdy, g1); g2 = fma(fb, bdz, g2);
+                    }
                 }
             }
-            const double rb = dm.radii[b];
-            if (kv) {   // nonbonded: the structure's Verlet list of bead b, entries slot, slot + PW, ...
-                const long long at = (rS + k0 + kl) * Np + b;
-                const int cnt = ta.vl_cnt[at];
-                const unsigned short *row = ta.vl_idx + at * (long long)EHIC_VL_CAP;
-                const bool all = cnt > EHIC_VL_CAP;          // overflow: sweep every partner
-                const int n = all ? N : cnt;
+            if (kv) {   // nonbonded: slot s takes list entries [8 s, 8 s + 8), then (long lists) 8 PW + s, 8 PW + s + PW, ...
+                const bool all = vcnt > EHIC_VL_CAP;          // overflow: sweep every partner
+                const int n = all ? N : vcnt;
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-                for (int s = slot; s < n; s += PW) {
-                    const int o = all ? s : (int)row[s];
-                    if (o == b) continue;
+                auto visit = [&](int o) {
                     const double *xo = sx + (o * Sc + kl) * 3;
                     const double dx = xo[0] - xb0, dy = xo[1] - xb1, dz = xo[2] - xb2;
                     const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    const double d0 = rb + dm.radii[o];
-                    if (s2 < d0 * d0) {
+                    const double d0 = rb + s_rad[o];
+                    if (s2 < d0 * d0 && o != b) {
                         const double rd = rsqrt_nr(s2);
                         const double a = d0 - s2 * rd, aa = a * a;
                         const double g = aa * a * rd;
                         a0 = fma(g, dx, a0); a1 = fma(g, dy, a1); a2 = fma(g, dz, a2);
                         e_nb += aa * aa;
                     }
+                };
+                if (all) {
+                    for (int o = slot; o < N; o += PW) visit(o);
+                } else {
+                    const unsigned ws[4] = {vfirst.x, vfirst.y, vfirst.z, vfirst.w};
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (8 * slot + u < n) visit((int)((ws[u >> 1] >> (16 * (u & 1))) & 0xffffu));
+                    for (int s = 8 * PW + slot; s < n; s += PW) visit((int)vrow[s]);
                 }
                 g0 = fma(sc_nb, a0, g0); g1 = fma(sc_nb, a1, g1); g2 = fma(sc_nb, a2, g2);
             }
@@ -274,16 +330,16 @@ trajectory_cluster_kernel(DevModel dm, LaneDev ld, TrajClusterArgs ta)
             if (slot != 0 || !kv) continue;                  // the first LK lanes finish the bead, one structure each
             {   // backbone: bonds (b-1, b) and (b, b+1)  (backbone_prior_c.pyx:26-42)
                 double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-                if (b > 0 && !isinf(dm.bb_ul[b - 1])) {
-                    const double ul = dm.bb_ul[b - 1], ll = dm.bb_ll[b - 1];
+                if (b > 0 && !isinf(s_ul[b - 1])) {
+                    const double ul = s_ul[b - 1], ll = s_ll[b - 1];
                     const double *xo = sx + ((b - 1) * Sc + kl) * 3;
                     const double d0 = xb0 - xo[0], d1 = xb1 - xo[1], d2 = xb2 - xo[2];
                     const double s2 = d0 * d0 + d1 * d1 + d2 * d2;
                     if (s2 > ul * ul) { const double d = sqrt(s2), a = d - ul; r0 = a * d0 / d; r1 = a * d1 / d; r2 = a * d2 / d; e_bb += a * a; }
                     else if (s2 < ll * ll) { const double d = sqrt(s2), a = ll - d; r0 = -(a * d0 / d); r1 = -(a * d1 / d); r2 = -(a * d2 / d); e_bb += a * a; }
                 }
-                if (!isinf(dm.bb_ul[b])) {
-                    const double ul = dm.bb_ul[b], ll = dm.bb_ll[b];
+                if (!isinf(s_ul[b])) {
+                    const double ul = s_ul[b], ll = s_ll[b];
                     const double *xo = sx + ((b + 1) * Sc + kl) * 3;
                     const double d0 = xo[0] - xb0, d1 = xo[1] - xb1, d2 = xo[2] - xb2;
                     const double s2 = d0 * d0 + d1 * d1 + d2 * d2;
@@ -357,8 +413,8 @@ trajectory_cluster_kernel(DevModel dm, LaneDev ld, TrajClusterArgs ta)
 // dynamic shared memory of one CTA
 static inline size_t traj_cluster_smem(int N, int Sc, long long M, int chunk)
 {
-    return sizeof(double) * ((size_t)N * Sc * 3 + (size_t)M + 2 * (size_t)chunk + 32 + 40 + 32) + sizeof(unsigned long long) * 32 +
-           sizeof(int) * 40;
+    return sizeof(double) * ((size_t)N * Sc * 3 + (size_t)M + 2 * (size_t)chunk + 32 + 40 + 32 + 3 * (size_t)N) +
+           sizeof(unsigned long long) * 32 + sizeof(int) * (40 + 2 * (size_t)N + 2);
 }
 
 }  // namespace ehic

@@ -539,14 +539,15 @@ def test_cluster_trajectory_equals_multi_kernel_trajectory_and_oracle(monkeypatc
     assert abs(H[r, 1] - 0.5 * np.sum(p1 ** 2)) <= 1e-9 * H[r, 1] and abs(H[r, 3] - 0.5 * np.sum(p2 ** 2)) <= 1e-9 * H[r, 3]
 
 
-def test_cluster_trajectory_is_the_automatic_choice_for_the_nora2012_shape():
+def test_cluster_trajectory_on_the_nora2012_shape():
     """308 beads x 30 structures, M = 10 145 (config_files/nora2012/30structures_3kb.cfg): 222 KB of coordinates do not fit
-    one SM's shared memory beside the weights; the cluster kernel is picked without any override, for the full ladder
-    on one GPU (302 replicas) and for an eighth of it, and reproduces the multi-kernel trajectory"""
+    one SM's shared memory beside the weights.  EHIC_TRAJ=cluster runs a whole trajectory of that shape as ONE launch
+    (a cluster of 2, 4 or 8 CTAs per replica) and reproduces the multi-kernel trajectory; without the override the
+    captured multi-kernel graph stays the choice, because it measured faster at every batch size"""
     import os
     import torch
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nora2012.npz"))
-    from ensemble_hic_b200.engine import Model
+    from ensemble_hic_b200.engine import Model, launch_count
     R, L = 5, 8
     kw = dict(alpha=float(g["alpha"]), k_nb=float(g["k_nb"]), k_bb=float(g["k_bb"]), max_replicas=302)
     rng = np.random.default_rng(9)
@@ -556,24 +557,29 @@ def test_cluster_trajectory_is_the_automatic_choice_for_the_nora2012_shape():
     t = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device=dev)
     lam = np.linspace(0.2, 1.0, R); eps = np.full(R, 1e-3); nrm = np.full(R, float(g["norm"]))
     res = {}
-    for mode in ("auto", "multi"):
-        if mode == "multi":
-            os.environ["EHIC_TRAJ"] = "multi"
+    for mode in ("auto", "cluster", "multi"):
+        if mode != "auto":
+            os.environ["EHIC_TRAJ"] = mode
         try:
             m = Model(int(g["S"]), g["radii"], g["data"], g["cds"], **kw)
         finally:
             os.environ.pop("EHIC_TRAJ", None)
-        if mode == "auto":
-            for Rq in (302, 38):
-                plan = m.trajectory_plan(Rq, 100)
+        for Rq in (302, 38):
+            plan = m.trajectory_plan(Rq, 100)
+            if mode == "cluster":
                 assert plan["mode"] == "cluster" and plan["ctas_per_replica"] in (2, 4, 8) and plan["launches"] == 1, plan
+            else:
+                assert plan["mode"] == "graph", plan
         x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
+        l0 = launch_count()
         m.hmc_trajectory_device(R, L, x_t, p_t, t(nrm), t(lam), t(lam), t(eps), H_t)
         torch.cuda.synchronize()
-        res[mode] = (x_t.cpu().numpy(), p_t.cpu().numpy(), H_t.cpu().numpy())
+        res[mode] = (x_t.cpu().numpy(), p_t.cpu().numpy(), H_t.cpu().numpy(), launch_count() - l0)
         m.close()
-    assert relerr(res["auto"][0], res["multi"][0]) < 1e-12 and relerr(res["auto"][1], res["multi"][1]) < 1e-10
-    np.testing.assert_allclose(res["auto"][2], res["multi"][2], rtol=1e-11)
+    assert res["cluster"][3] == 1 and res["auto"][3] > 3 * L
+    for mode in ("auto", "cluster"):
+        assert relerr(res[mode][0], res["multi"][0]) < 1e-12 and relerr(res[mode][1], res["multi"][1]) < 1e-10
+        np.testing.assert_allclose(res[mode][2], res["multi"][2], rtol=1e-11)
 
 
 # ---- Verlet lists inside trajectories ---------------------------------------------------------------
