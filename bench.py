@@ -391,6 +391,24 @@ def bench_ladder(name, ctx, n_iter, L=100, swap_interval=5):
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["whole_trajectory"] = {"achieved": contact_flop / (traj_ms * 1e-3) / 1e12,
                                     "frac": contact_flop / (traj_ms * 1e-3) / 1e12 / roof["peak"]}
+        # optional FP32 mode (sparse lists: FP32 lane kernels) on the same trajectory, beside the FP64 figure
+        fp32_mode = None
+        try:
+            m32 = Model(S, g["radii"], data, g["cds"], max_replicas=max(R, 1), fp32=True, **kw)
+            x32, p32 = t(X0), t(rs.normal(size=X0.shape))
+            run32 = lambda: m32.hmc_trajectory_device(R, L, x32, p32, nrmw, lamw, lamw, epsw, Hw)
+            run32(); torch.cuda.synchronize()
+            a0.record()
+            for _ in range(3):
+                run32()
+            a1.record(); torch.cuda.synchronize()
+            ms32 = a0.elapsed_time(a1) / 3
+            fp32_mode = {"trajectory_ms": ms32, "ms_per_leapfrog_step": ms32 / (L + 1), "path": m32.info()["path"],
+                         "trajectory_mode": m32.trajectory_plan(max(R, 1), L)["mode"], "speedup_vs_f64": traj_ms / ms32,
+                         "dtype": "f32 pair arithmetic of the contact term, f64 I/O and priors"}
+            m32.close(); del x32, p32
+        except Exception as exc:                                    # reported, never fatal for the FP64 record
+            fp32_mode = {"error": str(exc)}
         sec = ms * 1e-3
         out = {"workload": "%s: %d beads x %d structures, M=%d, full ladder of %d temperatures partitioned over %d GPU(s), "
                            "L=%d, swap every %dth iteration, norm sampled" % (name, N, S, M, T, world, L, swap_interval),
@@ -403,7 +421,7 @@ def bench_ladder(name, ctx, n_iter, L=100, swap_interval=5):
                "hmc_acceptance": float(np.mean(rex.n_acc_T / np.maximum(rex.n_hmc_T, 1))),
                "re_acceptance": float(np.sum(rex.re_acc) / max(np.sum(rex.re_try), 1)),
                "timestep_range": [float(rex.timestep_T.min()), float(rex.timestep_T.max())],
-               "roofline": roof}
+               "roofline": roof, "fp32_mode": fp32_mode}
         if world == 1 and ctx["cpu"]:
             cores = _host_cores()
             rates = _pool_map(_ladder_cpu_worker, [(name, c, 4.0) for c in range(cores)], cores)

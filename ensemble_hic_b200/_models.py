@@ -19,7 +19,7 @@ _MAX = int(os.environ.get("EHIC_MODEL_CACHE", "8"))
 
 
 def default_fp32():
-    """EHIC_FP32=1 selects the optional FP32 pair arithmetic (dense contact lists only) for posteriors built
+    """EHIC_FP32=1 selects the optional FP32 pair arithmetic (tile kernels for dense contact lists, lane kernels for all others) for posteriors built
     by make_posterior."""
     return os.environ.get("EHIC_FP32", "0") not in ("0", "", "false", "False")
 

@@ -55,7 +55,7 @@ struct ehic_model {
     bool nb_fused = false;          // tiles cover all bead pairs: nonbonded force rides in the backward tile kernel
     const unsigned char *tile_clean = nullptr;
     TileDev td{};
-    bool f32 = false;               // EHIC_FLAG_FP32: FP32 pair arithmetic in the tile kernels
+    bool f32 = false;               // EHIC_FLAG_FP32: FP32 pair arithmetic in the tile kernels (dense lists) / lane kernels (all other lists)
     const float *dc32 = nullptr;    // [n_tiles*4096] contact distances as floats
     float *tw32 = nullptr;          // [R][n_tiles*4096] lammda * weight as floats
     bool use_lanes = false;         // sparse list + fast mode + enough structures to fill warps: lane path
@@ -294,11 +294,12 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         if (want && desc->n_data > 0) build_tiles(L, desc->data_points, desc->contact_distances, min_fill, TL);
         m->use_tiles = TL.eligible;
         m->tile_fill = TL.fill;
-        if (desc->flags & EHIC_FLAG_FP32) {
-            if (!TL.eligible) {
+        // FP32 mode: dense lists run the FP32 tile kernels, every other list the FP32 lane kernels (below)
+        if ((desc->flags & EHIC_FLAG_FP32) && desc->n_data > 0) {
+            if (!TL.eligible && path && !strcmp(path, "rows")) {
                 delete m;
-                return fail(EHIC_ERR_INVALID, "EHIC_FLAG_FP32 needs a dense contact list (tile path): " +
-                                              (TL.why.empty() ? std::string("tile path disabled") : TL.why));
+                return fail(EHIC_ERR_INVALID, "EHIC_FLAG_FP32 has no row-path kernels: unset EHIC_PATH=rows (dense lists take the tile "
+                                              "path, all others the lane path)");
             }
             m->f32 = true;
         }
@@ -339,6 +340,7 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
         bool want = (double)S >= 0.6 * 32.0 * nkg;
         if (path && !strcmp(path, "lanes")) want = true;
         if (path && !strcmp(path, "rows")) want = false;
+        if (m->f32) want = true;                               // the FP32 mode of sparse lists lives on the lane path
         if (m->use_tiles) want = false;
         // the cluster trajectory kernel walks the same CSR / pair views: its weight table (8 M bytes) must fit beside
         // the coordinates in shared memory, and Verlet lists index beads with 16 bits
@@ -374,6 +376,13 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
                     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return L.row_len[a] > L.row_len[b]; });
             }
             UPL(pairs, pairs); UPL(LL.slot_a, slot_a); UPL(LL.slot_b, slot_b); UPL(roff, row_off); UPL(ents, ent); UPL(order, order);
+            if (m->f32 && want) {                                  // float copies of the contact distances in both views
+                std::vector<LanePair32> p32(pairs.size());
+                for (size_t q = 0; q < pairs.size(); q++) { p32[q].i = pairs[q].i; p32[q].j = pairs[q].j; p32[q].dc = (float)pairs[q].dc; p32[q].pad = 0; }
+                std::vector<LaneEnt32> e32(ents.size());
+                for (size_t q = 0; q < ents.size(); q++) { e32[q].dc = (float)ents[q].dc; e32[q].j = ents[q].j; }
+                UPL(p32, pairs32); UPL(e32, ent32);
+            }
 #undef UPL
             m->use_lanes = want;
             m->tc_possible = tc_want;
@@ -610,7 +619,7 @@ static int launch_pack(ehic_model *m, int R, const double *d_x, double *xs, doub
     KernelTimer kt_(m, KC_PACK, st);
     if (m->use_lanes && xt) {
         dim3 grid((unsigned)(m->dm.Np / 32), (unsigned)m->ld.nkg, (unsigned)R);
-        pack_lane_kernel<<<grid, 256, 0, st>>>(d_x, xs, xt, m->dm.N, m->dm.Np, m->dm.S, m->ld.nkg);
+        pack_lane_kernel<<<grid, 256, 0, st>>>(d_x, xs, xt, m->dm.N, m->dm.Np, m->dm.S, m->ld.nkg, m->f32 ? 1 : 0);
         LAUNCHED();
         CU(cudaGetLastError());
         return EHIC_OK;
@@ -656,8 +665,12 @@ static int launch_forward(ehic_model *m, int R, const double *xs, const double *
     }
     dim3 grid((unsigned)m->nA, (unsigned)R);
     if (m->use_lanes) {
-        forward_lane_kernel<<<grid, 256, 0, st>>>(m->dm, m->ld, m->xt[m->cur_xt], d_norm, d_md, want_w ? m->wbuf : nullptr,
-                                                   m->partA, want_logl);
+        if (m->f32)
+            forward_lane32_kernel<<<grid, 256, 0, st>>>(m->dm, m->ld, m->xt[m->cur_xt], d_norm, d_md,
+                                                         want_w ? reinterpret_cast<float *>(m->wbuf) : nullptr, m->partA, want_logl);
+        else
+            forward_lane_kernel<<<grid, 256, 0, st>>>(m->dm, m->ld, m->xt[m->cur_xt], d_norm, d_md, want_w ? m->wbuf : nullptr,
+                                                       m->partA, want_logl);
         LAUNCHED();
         CU(cudaGetLastError());
         return EHIC_OK;
@@ -797,7 +810,8 @@ static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_
     KernelTimer kt_(m, KC_GATHER, st);
     if (m->use_lanes) {
         const unsigned blocks = (unsigned)((long long)R * m->ld.nkg * m->n_quads);
-        backward_lane_kernel<<<blocks, EHIC_LANE_WARPS * 32, 0, st>>>(m->dm, m->ld, ga, m->n_quads);
+        if (m->f32) backward_lane32_kernel<<<blocks, EHIC_LANE_WARPS * 32, 0, st>>>(m->dm, m->ld, ga, m->n_quads);
+        else backward_lane_kernel<<<blocks, EHIC_LANE_WARPS * 32, 0, st>>>(m->dm, m->ld, ga, m->n_quads);
         LAUNCHED();
         CU(cudaGetLastError());
         return EHIC_OK;
@@ -979,7 +993,7 @@ static size_t traj_small_smem(const ehic_model *m)
 }
 static bool traj_small_ok(const ehic_model *m)
 {
-    return traj_small_smem(m) <= 200 * 1024 && !(m->flags & EHIC_FLAG_EXACT) && !m->opt_traj_multi && !m->opt_traj_no_small &&
+    return traj_small_smem(m) <= 200 * 1024 && !(m->flags & EHIC_FLAG_EXACT) && !m->f32 && !m->opt_traj_multi && !m->opt_traj_no_small &&
            !m->profiling;
 }
 
@@ -1011,7 +1025,7 @@ static const ehic_model::TcPlan &plan_cluster(ehic_model *m, int R)
 {
     for (const auto &p : m->tc_plans) if (p.R == R) return p;
     ehic_model::TcPlan best; best.R = R;
-    const bool eligible = m->tc_possible && m->use_verlet && !(m->flags & EHIC_FLAG_EXACT) && !m->opt_traj_multi && m->opt_cluster != 0;
+    const bool eligible = m->tc_possible && m->use_verlet && !(m->flags & EHIC_FLAG_EXACT) && !m->f32 && !m->opt_traj_multi && m->opt_cluster != 0;
     if (eligible) {
         const int N = m->dm.N, S = m->dm.S; const long long M = m->dm.M;
         double best_cost = 1e300;

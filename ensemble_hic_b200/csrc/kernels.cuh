@@ -177,7 +177,7 @@ __global__ void pack_kernel(const double *__restrict__ x, double *__restrict__ x
 // structures and beads are written as zeros.
 __global__ void __launch_bounds__(256)
 pack_lane_kernel(const double *__restrict__ x, double *__restrict__ xs, double *__restrict__ xg,
-                 int N, int Np, int S, int nkg)
+                 int N, int Np, int S, int nkg, int f32 /* xg holds (hi, lo) float pairs: FP32 mode */)
 {
     __shared__ double t[32][97];
     const int i0 = blockIdx.x * 32, kg = blockIdx.y, r = blockIdx.z;
@@ -191,7 +191,10 @@ pack_lane_kernel(const double *__restrict__ x, double *__restrict__ xs, double *
     }
     __syncthreads();
     double *g = xg + (((long long)r * nkg + kg) * Np + i0) * 96;
-    for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) g[idx] = t[idx & 31][idx >> 5];
+    for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
+        const double v = t[idx & 31][idx >> 5];
+        g[idx] = f32 ? split_hilo(v) : v;
+    }
     for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
         const int b = idx & 31, kc = idx >> 5, k = kc / 3, c = kc - 3 * k;
         const int kgl = kg * 32 + k;
@@ -1284,6 +1287,8 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
 // No atomics; every output has one writer and a fixed order.
 struct __align__(16) LanePair { int i, j; double dc; };
 struct __align__(16) LaneEnt { double dc; int j; int pad; };
+struct __align__(16) LanePair32 { int i, j; float dc; int pad; };    // FP32 mode: the same views with float contact distances
+struct __align__(8) LaneEnt32 { float dc; int j; };
 
 struct LaneDev {
     int nkg;                        // structure groups of 32 lanes
@@ -1292,6 +1297,8 @@ struct LaneDev {
     const long long *row_off;       // [N+1] CSR: both directions of every pair
     const LaneEnt *ent;             // [2M]
     const int *order;               // [N] bead handled by backward work item q: identity, or longest rows first for ragged lists
+    const LanePair32 *pairs32;      // [M]  FP32 mode only
+    const LaneEnt32 *ent32;         // [2M] FP32 mode only
 };
 
 __device__ __forceinline__ void reduce8(double (&r)[8], int lane);      // defined with the tile kernels below
@@ -1382,13 +1389,56 @@ forward_lane_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, cons
     }
 }
 
+#define EHIC_LANE_WARPS 4
+// Epilogue shared by the FP64 and FP32 backward lane kernels: lammda * g + priors, optional leapfrog kick + drift
+// (the drifted positions go to both working copies; F32: the lane copy holds (hi, lo) float pairs), kinetic partials.
+template <bool F32>
+__device__ __forceinline__ void lane_epilogue(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, int r, int kg, int k, int b,
+                                              int lane, int warp, bool live, long long gstride,
+                                              double x0, double x1, double x2, double acc0, double acc1, double acc2)
+{
+    const double lam = ga.lammda ? ga.lammda[r] : 1.0;
+    double kin = 0.0;
+    if (live) {
+        const long long at = (((long long)r * dm.S + k) * dm.N + b) * 3;
+        double g0 = __dmul_rn(lam, acc0), g1 = __dmul_rn(lam, acc1), g2 = __dmul_rn(lam, acc2);
+        if (ga.gprior) {
+            g0 = __dadd_rn(g0, ga.gprior[at]); g1 = __dadd_rn(g1, ga.gprior[at + 1]); g2 = __dadd_rn(g2, ga.gprior[at + 2]);
+        }
+        if (ga.grad) { ga.grad[at] = g0; ga.grad[at + 1] = g1; ga.grad[at + 2] = g2; }
+        if (ga.p) {
+            const double eps = ga.eps[r];
+            double p0 = ga.p[at], p1 = ga.p[at + 1], p2 = ga.p[at + 2];
+            if (ga.kinetic_mode == 1) kin += p0 * p0 + p1 * p1 + p2 * p2;
+            const double ke = ga.kick * eps;
+            p0 = fma(-ke, g0, p0); p1 = fma(-ke, g1, p1); p2 = fma(-ke, g2, p2);
+            ga.p[at] = p0; ga.p[at + 1] = p1; ga.p[at + 2] = p2;
+            if (ga.kinetic_mode == 2) kin += p0 * p0 + p1 * p1 + p2 * p2;
+            if (ga.xs_next) {
+                if (F32) {                                   // the lane copy holds float pairs: exact positions from the SoA copy
+                    const double *xc = ga.xs_cur + ((long long)r * dm.S + k) * 3LL * dm.Np;
+                    x0 = xc[b]; x1 = xc[dm.Np + b]; x2 = xc[2 * dm.Np + b];
+                }
+                const double n0 = fma(eps, p0, x0), n1 = fma(eps, p1, x1), n2 = fma(eps, p2, x2);
+                double *xn = ga.xs_next + ((long long)r * dm.S + k) * 3LL * dm.Np;
+                xn[b] = n0; xn[dm.Np + b] = n1; xn[2 * dm.Np + b] = n2;
+                double *un = ga.xt_next + ((long long)r * ld.nkg + kg) * gstride + (long long)b * 96 + lane;
+                un[0] = F32 ? split_hilo(n0) : n0; un[32] = F32 ? split_hilo(n1) : n1; un[64] = F32 ? split_hilo(n2) : n2;
+            }
+        }
+    }
+    if (ga.partK) {
+        kin = warp_sum(kin);
+        if (lane == 0) ga.partK[(long long)blockIdx.x * EHIC_LANE_WARPS + warp] = kin;
+    }
+}
+
 // Backward, lane form: warp <-> (replica, structure group, bead b); lane <-> structure.  The warp
 // walks the CSR row of b -- (partner, contact distance) and the weight are broadcast loads, the
 // partner's coordinates three coalesced rows -- and accumulates g_b of its 32 structures in
 // registers: a gather, every pair evaluated from both ends, no atomics, fixed order.  CTA = 4
 // consecutive beads of one structure group, so neighbouring rows share partner lines in L1.
 // Epilogue as in gather_kernel (lammda * g + priors, optional leapfrog kick + drift).
-#define EHIC_LANE_WARPS 4
 __global__ void __launch_bounds__(EHIC_LANE_WARPS * 32)
 backward_lane_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
 {
@@ -1428,36 +1478,7 @@ backward_lane_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
             acc2 = fma(f, dz, acc2);
         }
     }
-    const double lam = ga.lammda ? ga.lammda[r] : 1.0;
-    double kin = 0.0;
-    if (k_ok && bead_ok) {
-        const long long at = (((long long)r * dm.S + k) * dm.N + b) * 3;
-        double g0 = __dmul_rn(lam, acc0), g1 = __dmul_rn(lam, acc1), g2 = __dmul_rn(lam, acc2);
-        if (ga.gprior) {
-            g0 = __dadd_rn(g0, ga.gprior[at]); g1 = __dadd_rn(g1, ga.gprior[at + 1]); g2 = __dadd_rn(g2, ga.gprior[at + 2]);
-        }
-        if (ga.grad) { ga.grad[at] = g0; ga.grad[at + 1] = g1; ga.grad[at + 2] = g2; }
-        if (ga.p) {
-            const double eps = ga.eps[r];
-            double p0 = ga.p[at], p1 = ga.p[at + 1], p2 = ga.p[at + 2];
-            if (ga.kinetic_mode == 1) kin += p0 * p0 + p1 * p1 + p2 * p2;
-            const double ke = ga.kick * eps;
-            p0 = fma(-ke, g0, p0); p1 = fma(-ke, g1, p1); p2 = fma(-ke, g2, p2);
-            ga.p[at] = p0; ga.p[at + 1] = p1; ga.p[at + 2] = p2;
-            if (ga.kinetic_mode == 2) kin += p0 * p0 + p1 * p1 + p2 * p2;
-            if (ga.xs_next) {
-                const double n0 = fma(eps, p0, x0), n1 = fma(eps, p1, x1), n2 = fma(eps, p2, x2);
-                double *xn = ga.xs_next + ((long long)r * dm.S + k) * 3LL * dm.Np;
-                xn[b] = n0; xn[dm.Np + b] = n1; xn[2 * dm.Np + b] = n2;
-                double *un = ga.xt_next + ((long long)r * ld.nkg + kg) * gstride + (long long)b * 96 + lane;
-                un[0] = n0; un[32] = n1; un[64] = n2;
-            }
-        }
-    }
-    if (ga.partK) {
-        kin = warp_sum(kin);
-        if (lane == 0) ga.partK[(long long)blockIdx.x * EHIC_LANE_WARPS + warp] = kin;
-    }
+    lane_epilogue<false>(dm, ld, ga, r, kg, k, b, lane, warp, k_ok && bead_ok, gstride, x0, x1, x2, acc0, acc1, acc2);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -2178,6 +2199,147 @@ backward_tile32_kernel(DevModel dm, TileDev td, BackwardTile32Args ba)
             if (b < dm.N) { double *o = ba.Grow + (rk * dm.N + b) * 3; o[0] = acc64[rb][0]; o[1] = acc64[rb][1]; o[2] = acc64[rb][2]; }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// FP32 mode of the LANE path (sparse lists; EHIC_FLAG_FP32, north star: 1e-5 relative).  Same mapping and
+// summation structure as forward_lane_kernel / backward_lane_kernel; the pair arithmetic runs on the FP32 pipe
+// with the same safeguards as the FP32 tile kernels: the lane copy xg holds (hi, lo) float pairs and differences
+// are (hi - hi) + (lo - lo); the contact function of far-apart pairs avoids the 1 + t/q cancellation; per-pair sums
+// over the ensemble stay in FP32 (S terms); the force accumulators of a bead are flushed into FP64 every 64 row
+// entries.  Contact distances come from float copies of the two list views, weights travel as floats in the
+// weight buffer; mock counts, Poisson weights, energies, priors and the leapfrog update stay FP64.
+__global__ void __launch_bounds__(256, 3)
+forward_lane32_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, const double *__restrict__ norm,
+                      double *__restrict__ md_out, float *__restrict__ wbuf32,
+                      double *__restrict__ partA, int want_logl)
+{
+    const int r = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long m0 = ((long long)blockIdx.x * 8 + warp) * 32;
+    const double nrm = norm[r];
+    const float alpha = (float)dm.alpha;
+    const long long gstride = (long long)dm.Np * 96;
+    const float2 *xr = reinterpret_cast<const float2 *>(xg) + (long long)r * ld.nkg * gstride + lane;
+    double term = 0.0;
+    if (m0 < dm.M) {                                    // warp-uniform
+        float tot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const long long mb = m0 + b * 8;
+            if (mb < dm.M) {                            // warp-uniform
+                float acc[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) acc[e] = 0.f;
+                for (int kg = 0; kg < ld.nkg; kg++) {
+                    const float2 *xk = xr + kg * gstride;
+                    const bool kv = kg * 32 + lane < dm.S;
+                    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
+                    int ci = -1;
+                    int4 pr[8];                         // (i, j, dc, -): re-read per structure group (L1-resident broadcast loads)
+#pragma unroll
+                    for (int e = 0; e < 8; e++) pr[e] = __ldg(reinterpret_cast<const int4 *>(ld.pairs32 + min(mb + e, dm.M - 1)));
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        if (pr[e].x != ci) {            // warp-uniform
+                            ci = pr[e].x;
+                            const float2 *p = xk + (long long)ci * 96;
+                            a0 = p[0]; a1 = p[32]; a2 = p[64];
+                        }
+                        const float2 *q = xk + (long long)pr[e].y * 96;
+                        const float2 q0 = q[0], q1 = q[32], q2 = q[64];
+                        const float dx = (a0.x - q0.x) + (a0.y - q0.y);
+                        const float dy = (a1.x - q1.x) + (a1.y - q1.y);
+                        const float dz = (a2.x - q2.x) + (a2.y - q2.y);
+                        const float s2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        const float rd = rsqrt_f32(s2);
+                        const float tt = alpha * (__int_as_float(pr[e].z) - s2 * rd);
+                        const float rq = rsqrt_f32_raw(fmaf(tt, tt, 1.0f));
+                        const float a = fabsf(tt) * rq;      // |t| / q in [0, 1)
+                        const float den = 1.0f + a;
+                        const float sv = tt >= 0.0f ? den : (rq * rq) * rcp_f32_raw(den);
+                        acc[e] += kv ? sv : 0.0f;
+                    }
+                }
+                reduce8_t(acc, lane);                   // lane L holds the total of pair mb + (L >> 2)
+                tot[b] = acc[0];
+            }
+        }
+        // lane L finishes pair m0 + 8 (L & 3) + (L >> 2)
+        const int bsel = lane & 3;
+        const float sum = bsel == 0 ? tot[0] : (bsel == 1 ? tot[1] : (bsel == 2 ? tot[2] : tot[3]));
+        const long long m = m0 + 8 * bsel + (lane >> 2);
+        if (m < dm.M) {
+            const double c = dm.pcnt[m];
+            const double md = (double)sum * (0.5 * nrm);
+            if (md_out) md_out[(long long)r * dm.M + dm.perm[m]] = md;
+            const double em = __dsub_rn(1.0, __ddiv_rn(c, md));
+            const float w = (float)__dmul_rn(__dmul_rn(__dmul_rn(0.5, em), nrm), dm.alpha);
+            if (wbuf32) {
+                float *wr = wbuf32 + (long long)r * dm.wstride * 2;      // the replica's slice of the (double-sized) weight buffer
+                wr[ld.slot_a[m]] = w;
+                wr[ld.slot_b[m]] = w;
+            }
+            if (want_logl) term = c * log(md) - md;
+        }
+    }
+    if (want_logl) {
+        __shared__ double sh[8];
+        double v = warp_sum(term);
+        if (lane == 0) sh[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            partA[(long long)r * gridDim.x + blockIdx.x] = ((sh[0] + sh[1]) + (sh[2] + sh[3])) + ((sh[4] + sh[5]) + (sh[6] + sh[7]));
+    }
+}
+
+__global__ void __launch_bounds__(EHIC_LANE_WARPS * 32)
+backward_lane32_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int quad = blockIdx.x % n_quads;
+    const int tmp = blockIdx.x / n_quads;
+    const int kg = tmp % ld.nkg;
+    const int r = tmp / ld.nkg;
+    const int item = quad * EHIC_LANE_WARPS + warp;
+    const bool bead_ok = item < dm.N;
+    const int b = bead_ok ? ld.order[item] : dm.N - 1;
+    const int k = kg * 32 + lane;
+    const bool k_ok = k < dm.S;
+    const long long gstride = (long long)dm.Np * 96;
+    const float2 *xk = reinterpret_cast<const float2 *>(ga.xt) + ((long long)r * ld.nkg + kg) * gstride + lane;
+    const float2 x0 = xk[(long long)b * 96], x1 = xk[(long long)b * 96 + 32], x2 = xk[(long long)b * 96 + 64];
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    if (ga.contact && dm.M > 0 && bead_ok) {            // warp-uniform
+        const long long e0 = ld.row_off[b], e1 = ld.row_off[b + 1];
+        const float *wr = reinterpret_cast<const float *>(ga.wbuf) + (long long)r * dm.wstride * 2;
+        const float alpha = (float)dm.alpha;
+        float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+        for (long long eb = e0; eb < e1; eb += 64) {    // FP32 partial sums of at most 64 entries
+            const long long ee = min(eb + 64, e1);
+#pragma unroll 4
+            for (long long e = eb; e < ee; e++) {
+                const int2 v = __ldg(reinterpret_cast<const int2 *>(ld.ent32 + e));
+                const float dc = __int_as_float(v.x);
+                const float w = wr[e];
+                const float2 *q = xk + (long long)v.y * 96;
+                const float2 q0 = q[0], q1 = q[32], q2 = q[64];
+                const float dx = (q0.x - x0.x) + (q0.y - x0.y);
+                const float dy = (q1.x - x1.x) + (q1.y - x1.y);
+                const float dz = (q2.x - x2.x) + (q2.y - x2.y);
+                const float s = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                const float rd = rsqrt_f32(s);
+                const float tt = alpha * (dc - s * rd);
+                const float rq = rsqrt_f32_raw(fmaf(tt, tt, 1.0f));
+                const float f = w * ((rq * rq) * (rq * rd));
+                f0 = fmaf(f, dx, f0); f1 = fmaf(f, dy, f1); f2 = fmaf(f, dz, f2);
+            }
+            acc0 += (double)f0; acc1 += (double)f1; acc2 += (double)f2;
+            f0 = f1 = f2 = 0.f;
+        }
+    }
+    // positions for the drift come from the FP64 SoA copy inside the epilogue
+    lane_epilogue<true>(dm, ld, ga, r, kg, k, b, lane, warp, k_ok && bead_ok, gstride, 0.0, 0.0, 0.0, acc0, acc1, acc2);
 }
 
 // Combine + epilogue of the tile path: thread <-> (replica, structure, bead).

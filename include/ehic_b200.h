@@ -55,8 +55,9 @@ extern "C" {
                                    are reproduced bit for bit (slower; the default "fast" mode
                                    uses Newton-refined rsqrt and is within ~1e-13 relative) */
 #define EHIC_FLAG_FP32       2  /* optional FP32 pair arithmetic of the contact term (1e-5 relative), FP64 I/O
-                                   and priors; needs a dense contact list (tile path), else
-                                   ehic_model_create fails with EHIC_ERR_INVALID; excludes EHIC_FLAG_EXACT */
+                                   and priors; dense contact lists run the FP32 tile kernels, all other lists
+                                   the FP32 lane kernels (whole trajectories then run as the multi-kernel graph:
+                                   the one-launch trajectory kernels are FP64 only); excludes EHIC_FLAG_EXACT */
 #define EHIC_FLAG_NB_CELLS   4  /* nonbonded term through a cell grid instead of tiled all-pairs */
 
 /* indices into the per-replica energy vector written by ehic_evaluate */

@@ -318,14 +318,90 @@ def test_fp32_mode_within_1e5_of_oracle(co, monkeypatch, S, N, density, shift):
     assert 1e-9 < relerr(out["grad"], g64) < FP32_TOL
 
 
-def test_fp32_mode_needs_a_dense_list_and_excludes_exact():
-    from ensemble_hic_b200.engine import Model
-    sparse = make_problem(seed=3, S=2, N=256, density=0.1)
-    with pytest.raises(Exception, match="dense contact list"):
-        _model(sparse, False, fp32=True)
+def test_fp32_mode_excludes_exact_and_the_row_path(monkeypatch):
     dense = make_problem(seed=3, S=2, N=128, density=1.0)
     with pytest.raises(Exception, match="exclude"):
         _model(dense, True, fp32=True)
+    sparse = make_problem(seed=3, S=2, N=256, density=0.1)
+    monkeypatch.setenv("EHIC_PATH", "rows")
+    with pytest.raises(Exception, match="no row-path kernels"):
+        _model(sparse, False, fp32=True)
+
+
+@pytest.mark.parametrize("S,N,density,min_sep,shift", [(30, 64, 0.3, 1, 0.0), (33, 50, 0.5, 1, 0.0), (20, 100, 0.1, 2, 300.0),
+                                                       (2, 60, 0.4, 1, 0.0), (100, 37, 0.6, 1, -1000.0), (32, 200, 0.02, 3, 0.0)])
+def test_fp32_mode_sparse_lists_within_1e5_of_oracle(co, S, N, density, min_sep, shift):
+    """sparse lists in FP32 mode run the FP32 lane kernels whatever the ensemble size (S = 2 fills two lanes);
+    `shift` moves the ensemble away from the origin"""
+    from oracle.oracle import OraclePosterior
+    pb = make_problem(seed=S * 1000 + N, S=S, N=N, density=density, min_sep=min_sep, uniform_radii=False, step=0.7)
+    ul = pb["radii"][:-1] + pb["radii"][1:]
+    op = OraclePosterior(S, pb["data"], pb["cds"], pb["alpha"], pb["radii"], 50.0, 500.0,
+                         [np.zeros(N - 1)], [ul], [0, N], nonbonded="n2")
+    R = 3
+    rng = np.random.default_rng(1)
+    X = np.stack([pb["X"] + rng.normal(scale=0.03, size=pb["X"].shape) for _ in range(R)]) + shift
+    norm = rng.uniform(1, 5, R); lam = np.array([0.2, 1.0, 0.6]); bet = np.array([1.0, 0.3, 0.0])
+    m = _model(pb, False, max_replicas=R, fp32=True)
+    assert m.info()["path"] == "lanes" and m.info()["flags"] & 2
+    out = m.evaluate(X, norm, lam, bet, energies=True, md=True)
+    for r in range(R):
+        ref_md = op.mock_data(X[r], norm[r])
+        np.testing.assert_allclose(out["md"][r], ref_md, rtol=2e-5)
+        assert relerr(out["grad"][r], op.gradient(X[r], norm[r], lam[r], bet[r])) < FP32_TOL
+        E = op.energies(X[r], norm[r])
+        assert abs(out["energies"][r, 0] - E[0]) <= FP32_TOL * abs(E[0])
+        np.testing.assert_allclose(out["energies"][r, 1:], E[1:], rtol=1e-11)
+    glik = m.evaluate(X[0], norm[0], terms=1)["grad"][0]
+    assert relerr(glik, co.calculate_gradient(X[0], pb["alpha"], norm[0], pb["cds"], pb["data"])) < FP32_TOL
+    m64 = _model(pb, False, max_replicas=R)
+    g64 = m64.evaluate(X, norm, lam, bet)["grad"]
+    assert 1e-9 < relerr(out["grad"], g64) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", ["hairpin_s", "proteins", "nora2012"])
+def test_fp32_mode_on_the_golden_configs(name):
+    """the three shipped configurations (all sparse or small): FP32 mode against the reference's own outputs"""
+    import os
+    from ensemble_hic_b200.engine import Model
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    sphere = (float(g["sphere"][0]), float(g["sphere"][1]), np.zeros(3)) if len(g["sphere"]) else None
+    m = Model(int(g["S"]), g["radii"], g["data"], g["cds"], alpha=float(g["alpha"]), k_nb=float(g["k_nb"]), k_bb=float(g["k_bb"]),
+              sphere=sphere, fp32=True)
+    assert m.info()["path"] in ("lanes", "tiles") and m.info()["flags"] & 2
+    out = m.evaluate(g["X"].reshape(1, -1), float(g["norm"]), float(g["lammda"]), float(g["beta"]), energies=True, md=True)
+    np.testing.assert_allclose(out["md"][0], g["md"], rtol=2e-5)
+    assert relerr(out["grad"][0], g["grad"]) < FP32_TOL
+    glik = m.evaluate(g["X"].reshape(1, -1), float(g["norm"]), terms=1)["grad"][0]
+    assert relerr(glik, g["grad_lik"]) < FP32_TOL
+    assert abs(out["energies"][0, 0] - g["energies"][0]) <= FP32_TOL * abs(g["energies"][0])
+
+
+def test_fp32_mode_sparse_trajectory(monkeypatch):
+    """a leapfrog trajectory on the FP32 lane kernels (captured multi-kernel graph) stays within 1e-5 of the FP64 one"""
+    import torch
+    pb = make_problem(seed=78, S=20, N=90, density=0.3, step=0.8)
+    R, L = 2, 6
+    rng = np.random.default_rng(0)
+    X = np.stack([pb["X"], pb["X"] + rng.normal(scale=0.05, size=pb["X"].shape)]).reshape(R, -1)
+    P = rng.normal(size=X.shape)
+    norm = np.array([2.5, 3.5]); lam = np.array([0.3, 1.0]); bet = np.array([0.5, 1.0]); eps = np.array([5e-4, 1e-3])
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    res = {}
+    for fp32 in (False, True):
+        m = _model(pb, False, max_replicas=R, fp32=fp32)
+        assert m.trajectory_plan(R, L)["mode"] == ("graph" if fp32 else m.trajectory_plan(R, L)["mode"])
+        x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
+        for rep in range(2):
+            m.hmc_trajectory_device(R, L, x_t, p_t, t(norm), t(lam), t(bet), t(eps), H_t)
+        torch.cuda.synchronize()
+        res[fp32] = (x_t.cpu().numpy(), p_t.cpu().numpy(), H_t.cpu().numpy())
+        m.close()
+    assert relerr(res[True][0], res[False][0]) < 1e-8
+    assert relerr(res[True][1], res[False][1]) < FP32_TOL
+    np.testing.assert_allclose(res[True][2], res[False][2], rtol=FP32_TOL)
+    assert not np.array_equal(res[True][1], res[False][1])
 
 
 def test_fp32_mode_trajectory(monkeypatch):
