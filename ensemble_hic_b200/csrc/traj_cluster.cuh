@@ -16,8 +16,7 @@
 //     (remote stores), cluster barrier, the owner adds the C partials in rank order (deterministic), forms the Poisson
 //     weight (likelihoods_c.pyx:24-25,69) and stores it into the weight table W[M] of ALL CTAs (remote stores).
 //     Chunks are double-buffered: one cluster barrier per chunk plus one before the gradient phase;
-//   * the gradient phase is local to a CTA: warp <-> bead (longest contact rows first, handed out through a shared
-//     counter), gather form over the bead's CSR row (likelihoods_c.pyx:62-73, every pair visited from both beads: no
+//   * the gradient phase is local to a CTA: warp <-> bead (longest contact rows first, dealt round robin), gather form over the bead's CSR row (likelihoods_c.pyx:62-73, every pair visited from both beads: no
 //     atomics on floating-point data, fixed summation order), weights from W, then the nonbonded term from per-structure
 //     Verlet lists (global memory, one 128-byte line per bead; rebuilt inside the kernel when a conservative bound on
 //     the displacement since the last build exceeds skin / 2), backbone and sphere terms, kick.  Momenta live in
@@ -234,18 +233,16 @@ trajectory_cluster_kernel(DevModel dm, LaneDev ld, TrajClusterArgs ta)
                 }
             }
         }
-        if (tid == 0) s_int[0] = 0;                      // bead counter of the gradient phase
         cluster.sync();                                  // W complete everywhere
 
         // ======== gradient of every (structure, bead) of this CTA + kick ===============================================
         double e_nb = 0.0, e_bb = 0.0, e_sp = 0.0, kin = 0.0, pmax2 = 0.0;
         const double kick = (ends ? 0.5 : 1.0) * eps;
         const double sc_nb = bet * (dm.k_nb * 2.0);
-        for (;;) {
-            int it = 0;
-            if (lane == 0) it = atomicAdd(&s_int[0], 1);
-            it = __shfl_sync(0xffffffffu, it, 0);
-            if (it >= N) break;
+        // beads are dealt to the warps round robin in longest-row-first order: a STATIC assignment, so that the per-thread
+        // energy partials (and with them H) are summed in the same order in every run -- a shared work counter balanced
+        // the warps slightly better but made the last bits of H depend on the scheduling
+        for (int it = warp; it < N; it += NW) {
             const int b = s_ord[it];
             const double *xbp = sx + (b * Sc + kq) * 3;
             const double xb0 = xbp[0], xb1 = xbp[1], xb2 = xbp[2];
