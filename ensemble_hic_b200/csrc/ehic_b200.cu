@@ -61,6 +61,9 @@ struct ehic_model {
     bool use_lanes = false;         // sparse list + fast mode + enough structures to fill warps: lane path
     LaneDev ld{};
     int n_quads = 0;                // lane path: backward CTAs per (replica, structure group)
+    const long long *lane_cum = nullptr;   // [nkg * n_quads + 1] cumulative CSR entries of a replica's backward virtual blocks
+    bool lane_res_fwd = false, lane_res_bwd = false;   // replica-resident launches (a replica's lane copy fits one SM's L1)
+    int n_sm = 0;
     double tile_fill = 0.0;
     int nA_tile = 0, nKc = 0;       // forward-tile blocks per replica; combine blocks per structure
     double *tw = nullptr, *Grow = nullptr, *Pbuf = nullptr;
@@ -84,6 +87,7 @@ struct ehic_model {
     std::vector<TcPlan> tc_plans;   // per batch size R
     bool tc_attr[4] = {false, false, false, false};
     bool use_verlet = false;        // HMC trajectories: nonbonded term from Verlet lists reused across leapfrog steps
+    bool vl_fused = true;           // one verlet_step_kernel per leapfrog step (EHIC_VERLET_FUSED=0: check / build / sweep / force kernels)
     VerletDev vl{};
     double *partA = nullptr, *partP = nullptr, *partK = nullptr;
     double *energies = nullptr, *kinetic = nullptr;
@@ -387,6 +391,33 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
             m->use_lanes = want;
             m->tc_possible = tc_want;
             m->n_quads = (N + EHIC_LANE_WARPS - 1) / EHIC_LANE_WARPS;
+            if (want) {
+                // replica-resident launches (kernels.cuh, lane_resident_range): chosen when the lane copy a pass walks --
+                // one structure group in the backward pass, all of them in the forward pass -- fits one SM's L1
+                // (EHIC_LANE_RESIDENT=0 / 1 / 2: off / forward / forward and backward; EHIC_LANE_L1_KB: the capacity assumed, default 248)
+                std::vector<long long> cum((size_t)nkg * m->n_quads + 1, 0);
+                for (int kgq = 0; kgq < nkg; kgq++)
+                    for (int q = 0; q < m->n_quads; q++) {
+                        long long w = 0;
+                        for (int u = 0; u < EHIC_LANE_WARPS; u++) {
+                            const int it = q * EHIC_LANE_WARPS + u;
+                            if (it < N) w += L.row_len[order[it]] + 8;          // + the bead's epilogue
+                        }
+                        cum[(size_t)kgq * m->n_quads + q + 1] = cum[(size_t)kgq * m->n_quads + q] + w;
+                    }
+                rc = upload(m, cum, &m->lane_cum); if (rc) { ehic_model_destroy(m); return rc; }
+                cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, device);
+                const char *lr = getenv("EHIC_LANE_RESIDENT"), *lk = getenv("EHIC_LANE_L1_KB");
+                const size_t cap = (size_t)(lk ? atoi(lk) : 248) * 1024, one = (size_t)dm.Np * 768;
+                // measured on nora2012 (302 replicas, one B200): forward 0.350 -> 0.314 ms per step (93 % L1 hits, L2 sectors / 4);
+                // the backward pass gets 87 % L1 hits too but runs 0.556 -> 0.699 ms (8 warps per scheduler instead of 9, static
+                // ranges instead of the hardware's dynamic CTA dispatch), so only the forward pass takes it by default
+                m->lane_res_bwd = lr ? atoi(lr) == 2 : false;
+                m->lane_res_fwd = lr ? atoi(lr) != 0 : one * nkg <= cap;
+                for (auto f : {(const void *)forward_lane_resident_kernel, (const void *)forward_lane32_resident_kernel,
+                               (const void *)backward_lane_resident_kernel, (const void *)backward_lane32_resident_kernel})
+                    cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 0);      // all of it as L1
+            }
         }
     }
     // free the big host vectors we no longer need
@@ -448,6 +479,13 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
             if (cudaMemset(ip, 0, sizeof(int) * Rm * S * (size_t)(2 + dm.Np)) != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed"); }
             m->vl.state = ip; m->vl.stale = ip + Rm * S; m->vl.cnt = ip + 2 * Rm * S; m->vl.idx = reinterpret_cast<unsigned short *>(ip + Rm * S * (size_t)(2 + dm.Np + 32) / 32 * 32);     // 128-byte aligned
             DA(m->vl.xref, xs_n);
+            { const char *vf = getenv("EHIC_VERLET_FUSED"); m->vl_fused = !(vf && !strcmp(vf, "0")); }
+            const int vsm = (int)(sizeof(double) * 4 * (size_t)dm.Np);
+            cudaError_t ev = cudaFuncSetAttribute(verlet_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);
+            if (ev == cudaSuccess) ev = cudaFuncSetAttribute(verlet_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);
+            if (ev == cudaSuccess) ev = cudaFuncSetAttribute(verlet_step_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);
+            if (ev == cudaSuccess) ev = cudaFuncSetAttribute(verlet_step_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);
+            if (ev != cudaSuccess) { cudaGetLastError(); m->vl_fused = false; }
         }
     }
     DA(m->partA, Rm * (size_t)std::max(m->nA, 1));
@@ -665,7 +703,16 @@ static int launch_forward(ehic_model *m, int R, const double *xs, const double *
     }
     dim3 grid((unsigned)m->nA, (unsigned)R);
     if (m->use_lanes) {
-        if (m->f32)
+        const long long nv = (long long)R * m->nA;
+        if (m->lane_res_fwd && nv >= 2LL * m->n_sm) {              // a replica's pairs on one SM: its lane copy stays in L1
+            LaneSched sc{EHIC_LANE_FWD_GROUPS, nv, m->nA, nullptr};
+            if (m->f32)
+                forward_lane32_resident_kernel<<<m->n_sm, EHIC_LANE_FWD_GROUPS * 256, 0, st>>>(
+                    m->dm, m->ld, sc, m->xt[m->cur_xt], d_norm, d_md, want_w ? reinterpret_cast<float *>(m->wbuf) : nullptr, m->partA, want_logl);
+            else
+                forward_lane_resident_kernel<<<m->n_sm, EHIC_LANE_FWD_GROUPS * 256, 0, st>>>(
+                    m->dm, m->ld, sc, m->xt[m->cur_xt], d_norm, d_md, want_w ? m->wbuf : nullptr, m->partA, want_logl);
+        } else if (m->f32)
             forward_lane32_kernel<<<grid, 256, 0, st>>>(m->dm, m->ld, m->xt[m->cur_xt], d_norm, d_md,
                                                          want_w ? reinterpret_cast<float *>(m->wbuf) : nullptr, m->partA, want_logl);
         else
@@ -709,6 +756,22 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
     // boxes -- list rebuilds are rare and the box kernel costs more per step than its pruning saves per rebuild
     // (nora2012: 0.41 -> 0.37 ms per step); for long chains the pruned rebuild wins (config D: RE sweeps 1.765
     // with boxes, 1.738 without)
+    if (verlet && m->vl_fused && !cells) {
+        // one launch per step: displacement check, conditional list rebuild, list (or overflow all-pairs) force, backbone,
+        // sphere and the energy sums of every structure (kernels.cuh: verlet_step_kernel)
+        const unsigned n_struct = (unsigned)((long long)R * m->dm.S);
+        const size_t vsm = sizeof(double) * 4 * (size_t)m->dm.Np;
+        double *pc = want_energy ? m->partC : nullptr;
+        if (want_energy) CU(cudaMemsetAsync(m->partP, 0, sizeof(double) * 3 * (size_t)R * m->dm.S * m->nPx, st));   // nothing from prior_kernel
+        const int N = m->dm.N;
+        if (N <= 128) verlet_step_kernel<128><<<n_struct, 128, vsm, st>>>(m->dm, m->vl, xs, d_beta, gp, pc, terms);
+        else if (N <= 256) verlet_step_kernel<256><<<n_struct, 256, vsm, st>>>(m->dm, m->vl, xs, d_beta, gp, pc, terms);
+        else if (N <= 384) verlet_step_kernel<384><<<n_struct, 384, vsm, st>>>(m->dm, m->vl, xs, d_beta, gp, pc, terms);
+        else verlet_step_kernel<512><<<n_struct, 512, vsm, st>>>(m->dm, m->vl, xs, d_beta, gp, pc, terms);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        return EHIC_OK;
+    }
     static const int vl_boxes = []() { const char *e = getenv("EHIC_VERLET_BOXES"); return e ? atoi(e) : -1; }();
     const bool no_boxes = verlet && (vl_boxes >= 0 ? vl_boxes == 0 : m->dm.N < 1024);
     const double *boxes = no_boxes ? nullptr : m->bbox;
@@ -810,7 +873,12 @@ static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_
     KernelTimer kt_(m, KC_GATHER, st);
     if (m->use_lanes) {
         const unsigned blocks = (unsigned)((long long)R * m->ld.nkg * m->n_quads);
-        if (m->f32) backward_lane32_kernel<<<blocks, EHIC_LANE_WARPS * 32, 0, st>>>(m->dm, m->ld, ga, m->n_quads);
+        if (m->lane_res_bwd && (long long)blocks >= 2LL * EHIC_LANE_BWD_GROUPS * m->n_sm) {
+            LaneSched sc{EHIC_LANE_BWD_GROUPS, (long long)blocks, m->ld.nkg * m->n_quads, m->lane_cum};
+            const int th = EHIC_LANE_BWD_GROUPS * EHIC_LANE_WARPS * 32;
+            if (m->f32) backward_lane32_resident_kernel<<<m->n_sm, th, 0, st>>>(m->dm, m->ld, sc, ga, m->n_quads);
+            else backward_lane_resident_kernel<<<m->n_sm, th, 0, st>>>(m->dm, m->ld, sc, ga, m->n_quads);
+        } else if (m->f32) backward_lane32_kernel<<<blocks, EHIC_LANE_WARPS * 32, 0, st>>>(m->dm, m->ld, ga, m->n_quads);
         else backward_lane_kernel<<<blocks, EHIC_LANE_WARPS * 32, 0, st>>>(m->dm, m->ld, ga, m->n_quads);
         LAUNCHED();
         CU(cudaGetLastError());

@@ -1272,6 +1272,125 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
 }
 
 // ---------------------------------------------------------------------------------------
+// verlet_step_kernel: the whole prior of one leapfrog step in ONE launch, CTA <-> (replica, structure).
+//
+// Replaces the chain verlet_check -> verlet_build -> prior_kernel (early exit) -> verlet_force of a trajectory step:
+// four launches of which three usually do nothing, and a force kernel that gathered partner coordinates from L2 a
+// pair at a time after sorting its beads with shared-memory atomics (nora2012, 302 replicas: 0.31 ms of a 1.25 ms step).
+// Here the structure's coordinates and radii are staged in shared memory once (coalesced), and the CTA
+//   1. measures the largest displacement since the list was built (block maximum);
+//   2. if the list is missing or stale, rebuilds it from shared memory -- thread <-> bead, all partners in ascending
+//      order, same test as verlet_build_kernel -- and stores the new reference positions.  More than EHIC_VL_CAP
+//      partners for some bead: state 2, and until the next trajectory (verlet_retry_kernel) the structure is swept
+//      all-pairs from shared memory, which is what prior_kernel's fast path computes (same pairs, ascending order);
+//   3. evaluates the nonbonded force of every bead from its list, then the backbone and sphere terms (bonded_terms),
+//      writes the prior gradient once and, on request, the three energy sums of the structure.
+// A thread reads back only list rows it wrote itself, so no grid-wide ordering is needed.  Energies: thread <-> bead
+// is static, the block sum has a fixed order.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+verlet_step_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, const double *__restrict__ beta,
+                   double *__restrict__ gprior, double *__restrict__ partC, int terms)
+{
+    extern __shared__ __align__(16) double vsm[];              // [4][Np]: x, y, z, radius
+    __shared__ double sh[3][THREADS / 32];
+    const long long rk = blockIdx.x;
+    const int r = (int)(rk / dm.S);
+    const int Np = dm.Np, N = dm.N, tid = threadIdx.x;
+    const double *xk = xs + rk * 3LL * Np;
+    double *sx = vsm, *srad = vsm + 3 * Np;
+    int st = vl.state[rk];
+    double *xr = vl.xref + rk * 3LL * Np;
+    double mx = 0.0;
+    for (int b = tid; b < Np; b += THREADS) {
+        const double x0 = xk[b], x1 = xk[Np + b], x2 = xk[2 * Np + b];
+        sx[b] = x0; sx[Np + b] = x1; sx[2 * Np + b] = x2;
+        srad[b] = dm.radii[min(b, N - 1)];
+        if (st == 1 && b < N) {
+            const double d0 = x0 - xr[b], d1 = x1 - xr[Np + b], d2 = x2 - xr[2 * Np + b];
+            const double d = fma(d2, d2, fma(d1, d1, d0 * d0));
+            mx = fmax(mx, (d == d) ? d : 1e300);               // NaN coordinates: rebuild (and let the sweep see them)
+        }
+    }
+    const bool moved = mx > 0.25 * vl.skin * vl.skin;
+    const bool stale = st == 0 || (st == 1 && __syncthreads_or(moved));      // st is CTA-uniform
+    if (st != 1) __syncthreads();                                            // shared coordinates complete
+    int *cnt = vl.cnt + rk * Np;
+    unsigned short *idx = vl.idx + rk * (long long)Np * EHIC_VL_CAP;
+    if (stale) {
+        bool over = false;
+        const double skin = vl.skin;
+        for (int b = tid; b < N; b += THREADS) {
+            const double xb0 = sx[b], xb1 = sx[Np + b], xb2 = sx[2 * Np + b], rb = srad[b];
+            unsigned short *row = idx + (long long)b * EHIC_VL_CAP;
+            int n = 0;
+            for (int o = 0; o < N; o++) {
+                const double dx = sx[o] - xb0, dy = sx[Np + o] - xb1, dz = sx[2 * Np + o] - xb2;
+                const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                const double lim = rb + srad[o] + skin;
+                if (!(s2 >= lim * lim) && o != b) {             // !(>=): NaN distances are listed, like the sweep would see them
+                    if (n < EHIC_VL_CAP) row[n] = (unsigned short)o;
+                    n++;
+                }
+            }
+            cnt[b] = min(n, EHIC_VL_CAP);
+            over = over || n > EHIC_VL_CAP;
+            xr[b] = xb0; xr[Np + b] = xb1; xr[2 * Np + b] = xb2;
+        }
+        st = __syncthreads_or(over) ? 2 : 1;
+        if (tid == 0) vl.state[rk] = st;
+    }
+    const double sc = (beta ? beta[r] : 1.0) * (dm.k_nb * 2.0);
+    double e_nb = 0.0, e_bb = 0.0, e_sp = 0.0;
+    for (int b = tid; b < N; b += THREADS) {
+        const double xb0 = sx[b], xb1 = sx[Np + b], xb2 = sx[2 * Np + b], rb = srad[b];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        auto visit = [&](int o) {
+            const double dx = sx[o] - xb0, dy = sx[Np + o] - xb1, dz = sx[2 * Np + o] - xb2;
+            const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            const double d0 = rb + srad[o];
+            if (s2 < d0 * d0) {
+                const double rd = rsqrt_nr(s2);
+                const double a = d0 - s2 * rd, aa = a * a;
+                const double g = aa * a * rd;
+                a0 = fma(g, dx, a0); a1 = fma(g, dy, a1); a2 = fma(g, dz, a2);
+                e_nb += aa * aa;
+            }
+        };
+        if (st == 2) {
+            for (int o = 0; o < N; o++) if (o != b) visit(o);
+        } else {
+            // ascending partner order, as in prior_kernel; the list of a bead is one 128-byte line, 8 indices per load
+            const int n = cnt[b];
+            const uint4 *row = reinterpret_cast<const uint4 *>(idx + (long long)b * EHIC_VL_CAP);
+            for (int u0 = 0; u0 < n; u0 += 8) {
+                const uint4 w = row[u0 >> 3];
+                const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (u0 + u < n) visit((int)((ws[u >> 1] >> (16 * (u & 1))) & 0xffffu));
+            }
+        }
+        double g0 = sc * a0, g1 = sc * a1, g2 = sc * a2;
+        bonded_terms(dm, sx, Np, b, true, b, xb0, xb1, xb2, rb, terms, g0, g1, g2, e_bb, e_sp);
+        if (gprior) {
+            double *o = gprior + (rk * N + b) * 3;
+            o[0] = g0; o[1] = g1; o[2] = g2;
+        }
+    }
+    if (partC) {
+        e_nb = warp_sum(e_nb); e_bb = warp_sum(e_bb); e_sp = warp_sum(e_sp);
+        if ((tid & 31) == 0) { sh[0][tid >> 5] = e_nb; sh[1][tid >> 5] = e_bb; sh[2][tid >> 5] = e_sp; }
+        __syncthreads();
+        if (tid == 0) {
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            for (int q = 0; q < THREADS / 32; q++) { t0 += sh[0][q]; t1 += sh[1][q]; t2 += sh[2][q]; }
+            partC[rk * 3] = t0; partC[rk * 3 + 1] = t1; partC[rk * 3 + 2] = t2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // LANE path (large sparse contact lists, fast arithmetic): lane <-> structure.
 //
 // A warp works on ONE bead pair for the 32 structures of a structure group at a time, so the pair's
@@ -1308,14 +1427,51 @@ __device__ __forceinline__ void reduce8(double (&r)[8], int lane);      // defin
 // warp with ONE halving butterfly (reduce8) per batch, and after 4 batches every lane finishes one
 // pair (mock count, Poisson weight into both CSR slots, log-likelihood term).  Bead i of
 // consecutive pairs is the same most of the time and stays in registers.
-__global__ void __launch_bounds__(256, 3)       // 80 registers: 24 warps per SM hide the L2 latency of the partner rows better than 16
-forward_lane_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, const double *__restrict__ norm,
-                    double *__restrict__ md_out, double *__restrict__ wbuf,
-                    double *__restrict__ partA, int want_logl)
+//
+// Work item = "virtual block" (replica r, block of 256 consecutive pairs).  Two launch shapes run the same body:
+// the plain grid (one CTA per virtual block) and the REPLICA-RESIDENT one (lane_resident below).
+struct LaneSched {
+    int n_sub;           // 256-thread (forward) / 128-thread (backward) groups per CTA of the resident launch
+    long long n_virtual; // virtual blocks of the whole launch
+    int per_replica;     // virtual blocks per replica (forward: nA; backward: nkg * n_quads)
+    const long long *cum;   // [per_replica + 1] cumulative work of a replica's virtual blocks (backward: CSR entries), or NULL
+};
+
+__device__ __forceinline__ void group_sync(int group, int n_threads)
+{   // named barrier of one thread group of a resident CTA (barrier 0 is __syncthreads)
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(n_threads) : "memory");
+}
+
+// Replica-resident launch: ONE CTA per SM, each walking a CONTIGUOUS range of virtual blocks -- i.e. of one or two
+// replicas -- with all its thread groups.  The lane copy of one (replica, structure group) of a medium system
+// (nora2012 3 kb: 308 beads x 768 B = 236 KB) then stays in that SM's L1 for the whole pass and every partner row is
+// fetched from L2 once per replica instead of once per pair (the plain grid spreads consecutive blocks of a replica over
+// all SMs: 6.5 - 8 TB/s of L2 -> SM traffic, which is what bounds it; profiles/r01_nora_lanepath.txt).  Ranges hold equal
+// WORK (cumulative row lengths), not equal block counts: the backward pass walks the beads longest row first.
+__device__ __forceinline__ void lane_resident_range(const LaneSched &sc, long long &v0, long long &v1)
 {
-    const int r = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long m0 = ((long long)blockIdx.x * 8 + warp) * 32;
+    const int G = gridDim.x, g = blockIdx.x;
+    if (!sc.cum) { v0 = sc.n_virtual * g / G; v1 = sc.n_virtual * (g + 1) / G; return; }
+    const long long per = sc.cum[sc.per_replica];
+    const long long n_rep = sc.n_virtual / sc.per_replica;
+    auto locate = [&](int q) -> long long {                        // first virtual block at or after work fraction q / G
+        if (q >= G) return sc.n_virtual;
+        const long long tgt = (long long)((double)per * (double)n_rep * ((double)q / (double)G));
+        const long long r = min(tgt / max(per, 1LL), n_rep - 1), w = tgt - r * per;
+        int lo = 0, hi = sc.per_replica;                           // smallest b with cum[b] >= w
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sc.cum[mid] >= w) hi = mid; else lo = mid + 1; }
+        return r * sc.per_replica + lo;
+    };
+    v0 = locate(g); v1 = locate(g + 1);
+}
+
+__device__ __forceinline__ void
+forward_lane_body(const DevModel &dm, const LaneDev &ld, const double *__restrict__ xg, const double *__restrict__ norm,
+                  double *__restrict__ md_out, double *__restrict__ wbuf,
+                  double *__restrict__ partA, int want_logl, int vblock, int r, int tid, int group, double *sh /* [8] */)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    const long long m0 = ((long long)vblock * 8 + warp) * 32;
     const double nrm = norm[r], alpha = dm.alpha;
     const long long gstride = (long long)dm.Np * 96;
     const double *xr = xg + (long long)r * ld.nkg * gstride + lane;
@@ -1380,12 +1536,37 @@ forward_lane_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, cons
         }
     }
     if (want_logl) {
-        __shared__ double sh[8];
         double v = warp_sum(term);
         if (lane == 0) sh[warp] = v;
-        __syncthreads();
-        if (threadIdx.x == 0)
-            partA[(long long)r * gridDim.x + blockIdx.x] = ((sh[0] + sh[1]) + (sh[2] + sh[3])) + ((sh[4] + sh[5]) + (sh[6] + sh[7]));
+        group_sync(group, 256);
+        if (tid == 0)
+            partA[(long long)r * ((dm.M + 255) / 256) + vblock] = ((sh[0] + sh[1]) + (sh[2] + sh[3])) + ((sh[4] + sh[5]) + (sh[6] + sh[7]));
+        group_sync(group, 256);                          // sh is reused by the group's next virtual block
+    }
+}
+
+__global__ void __launch_bounds__(256, 3)       // 80 registers: 24 warps per SM hide the L2 latency of the partner rows better than 16
+forward_lane_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, const double *__restrict__ norm,
+                    double *__restrict__ md_out, double *__restrict__ wbuf,
+                    double *__restrict__ partA, int want_logl)
+{
+    __shared__ double sh[8];
+    forward_lane_body(dm, ld, xg, norm, md_out, wbuf, partA, want_logl, blockIdx.x, blockIdx.y, threadIdx.x, 0, sh);
+}
+
+#define EHIC_LANE_FWD_GROUPS 3                   // resident launch: 3 x 256 threads per SM
+__global__ void __launch_bounds__(EHIC_LANE_FWD_GROUPS * 256, 1)
+forward_lane_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, const double *__restrict__ xg, const double *__restrict__ norm,
+                             double *__restrict__ md_out, double *__restrict__ wbuf,
+                             double *__restrict__ partA, int want_logl)
+{
+    __shared__ double sh[EHIC_LANE_FWD_GROUPS][8];
+    const int group = threadIdx.x >> 8, tid = threadIdx.x & 255;
+    long long v0, v1;
+    lane_resident_range(sc, v0, v1);
+    for (long long v = v0 + group; v < v1; v += EHIC_LANE_FWD_GROUPS) {
+        const int r = (int)(v / sc.per_replica), vb = (int)(v - (long long)r * sc.per_replica);
+        forward_lane_body(dm, ld, xg, norm, md_out, wbuf, partA, want_logl, vb, r, tid, group, sh[group]);
     }
 }
 
@@ -1393,7 +1574,7 @@ forward_lane_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, cons
 // Epilogue shared by the FP64 and FP32 backward lane kernels: lammda * g + priors, optional leapfrog kick + drift
 // (the drifted positions go to both working copies; F32: the lane copy holds (hi, lo) float pairs), kinetic partials.
 template <bool F32>
-__device__ __forceinline__ void lane_epilogue(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, int r, int kg, int k, int b,
+__device__ __forceinline__ void lane_epilogue(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, long long vblock, int r, int kg, int k, int b,
                                               int lane, int warp, bool live, long long gstride,
                                               double x0, double x1, double x2, double acc0, double acc1, double acc2)
 {
@@ -1429,7 +1610,7 @@ __device__ __forceinline__ void lane_epilogue(const DevModel &dm, const LaneDev 
     }
     if (ga.partK) {
         kin = warp_sum(kin);
-        if (lane == 0) ga.partK[(long long)blockIdx.x * EHIC_LANE_WARPS + warp] = kin;
+        if (lane == 0) ga.partK[vblock * EHIC_LANE_WARPS + warp] = kin;
     }
 }
 
@@ -1439,12 +1620,12 @@ __device__ __forceinline__ void lane_epilogue(const DevModel &dm, const LaneDev 
 // registers: a gather, every pair evaluated from both ends, no atomics, fixed order.  CTA = 4
 // consecutive beads of one structure group, so neighbouring rows share partner lines in L1.
 // Epilogue as in gather_kernel (lammda * g + priors, optional leapfrog kick + drift).
-__global__ void __launch_bounds__(EHIC_LANE_WARPS * 32)
-backward_lane_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
+__device__ __forceinline__ void
+backward_lane_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, int n_quads, long long vblock, int tid)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int quad = blockIdx.x % n_quads;
-    const int tmp = blockIdx.x / n_quads;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int quad = (int)(vblock % n_quads);
+    const int tmp = (int)(vblock / n_quads);
     const int kg = tmp % ld.nkg;
     const int r = tmp / ld.nkg;
     const int item = quad * EHIC_LANE_WARPS + warp;
@@ -1478,7 +1659,23 @@ backward_lane_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
             acc2 = fma(f, dz, acc2);
         }
     }
-    lane_epilogue<false>(dm, ld, ga, r, kg, k, b, lane, warp, k_ok && bead_ok, gstride, x0, x1, x2, acc0, acc1, acc2);
+    lane_epilogue<false>(dm, ld, ga, vblock, r, kg, k, b, lane, warp, k_ok && bead_ok, gstride, x0, x1, x2, acc0, acc1, acc2);
+}
+
+__global__ void __launch_bounds__(EHIC_LANE_WARPS * 32)
+backward_lane_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
+{
+    backward_lane_body(dm, ld, ga, n_quads, blockIdx.x, threadIdx.x);
+}
+
+#define EHIC_LANE_BWD_GROUPS 8                   // resident launch: 8 x 128 threads per SM
+__global__ void __launch_bounds__(EHIC_LANE_BWD_GROUPS * EHIC_LANE_WARPS * 32, 1)
+backward_lane_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, GatherArgs ga, int n_quads)
+{
+    const int group = threadIdx.x / (EHIC_LANE_WARPS * 32), tid = threadIdx.x % (EHIC_LANE_WARPS * 32);
+    long long v0, v1;
+    lane_resident_range(sc, v0, v1);
+    for (long long v = v0 + group; v < v1; v += EHIC_LANE_BWD_GROUPS) backward_lane_body(dm, ld, ga, n_quads, v, tid);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -2209,14 +2406,13 @@ backward_tile32_kernel(DevModel dm, TileDev td, BackwardTile32Args ba)
 // over the ensemble stay in FP32 (S terms); the force accumulators of a bead are flushed into FP64 every 64 row
 // entries.  Contact distances come from float copies of the two list views, weights travel as floats in the
 // weight buffer; mock counts, Poisson weights, energies, priors and the leapfrog update stay FP64.
-__global__ void __launch_bounds__(256, 3)
-forward_lane32_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, const double *__restrict__ norm,
-                      double *__restrict__ md_out, float *__restrict__ wbuf32,
-                      double *__restrict__ partA, int want_logl)
+__device__ __forceinline__ void
+forward_lane32_body(const DevModel &dm, const LaneDev &ld, const double *__restrict__ xg, const double *__restrict__ norm,
+                    double *__restrict__ md_out, float *__restrict__ wbuf32,
+                    double *__restrict__ partA, int want_logl, int vblock, int r, int tid, int group, double *sh /* [8] */)
 {
-    const int r = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long m0 = ((long long)blockIdx.x * 8 + warp) * 32;
+    const int lane = tid & 31, warp = tid >> 5;
+    const long long m0 = ((long long)vblock * 8 + warp) * 32;
     const double nrm = norm[r];
     const float alpha = (float)dm.alpha;
     const long long gstride = (long long)dm.Np * 96;
@@ -2284,21 +2480,45 @@ forward_lane32_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, co
         }
     }
     if (want_logl) {
-        __shared__ double sh[8];
         double v = warp_sum(term);
         if (lane == 0) sh[warp] = v;
-        __syncthreads();
-        if (threadIdx.x == 0)
-            partA[(long long)r * gridDim.x + blockIdx.x] = ((sh[0] + sh[1]) + (sh[2] + sh[3])) + ((sh[4] + sh[5]) + (sh[6] + sh[7]));
+        group_sync(group, 256);
+        if (tid == 0)
+            partA[(long long)r * ((dm.M + 255) / 256) + vblock] = ((sh[0] + sh[1]) + (sh[2] + sh[3])) + ((sh[4] + sh[5]) + (sh[6] + sh[7]));
+        group_sync(group, 256);
     }
 }
 
-__global__ void __launch_bounds__(EHIC_LANE_WARPS * 32)
-backward_lane32_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
+__global__ void __launch_bounds__(256, 3)
+forward_lane32_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, const double *__restrict__ norm,
+                      double *__restrict__ md_out, float *__restrict__ wbuf32,
+                      double *__restrict__ partA, int want_logl)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int quad = blockIdx.x % n_quads;
-    const int tmp = blockIdx.x / n_quads;
+    __shared__ double sh[8];
+    forward_lane32_body(dm, ld, xg, norm, md_out, wbuf32, partA, want_logl, blockIdx.x, blockIdx.y, threadIdx.x, 0, sh);
+}
+
+__global__ void __launch_bounds__(EHIC_LANE_FWD_GROUPS * 256, 1)
+forward_lane32_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, const double *__restrict__ xg, const double *__restrict__ norm,
+                               double *__restrict__ md_out, float *__restrict__ wbuf32,
+                               double *__restrict__ partA, int want_logl)
+{
+    __shared__ double sh[EHIC_LANE_FWD_GROUPS][8];
+    const int group = threadIdx.x >> 8, tid = threadIdx.x & 255;
+    long long v0, v1;
+    lane_resident_range(sc, v0, v1);
+    for (long long v = v0 + group; v < v1; v += EHIC_LANE_FWD_GROUPS) {
+        const int r = (int)(v / sc.per_replica), vb = (int)(v - (long long)r * sc.per_replica);
+        forward_lane32_body(dm, ld, xg, norm, md_out, wbuf32, partA, want_logl, vb, r, tid, group, sh[group]);
+    }
+}
+
+__device__ __forceinline__ void
+backward_lane32_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, int n_quads, long long vblock, int tid)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    const int quad = (int)(vblock % n_quads);
+    const int tmp = (int)(vblock / n_quads);
     const int kg = tmp % ld.nkg;
     const int r = tmp / ld.nkg;
     const int item = quad * EHIC_LANE_WARPS + warp;
@@ -2339,7 +2559,22 @@ backward_lane32_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
         }
     }
     // positions for the drift come from the FP64 SoA copy inside the epilogue
-    lane_epilogue<true>(dm, ld, ga, r, kg, k, b, lane, warp, k_ok && bead_ok, gstride, 0.0, 0.0, 0.0, acc0, acc1, acc2);
+    lane_epilogue<true>(dm, ld, ga, vblock, r, kg, k, b, lane, warp, k_ok && bead_ok, gstride, 0.0, 0.0, 0.0, acc0, acc1, acc2);
+}
+
+__global__ void __launch_bounds__(EHIC_LANE_WARPS * 32)
+backward_lane32_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
+{
+    backward_lane32_body(dm, ld, ga, n_quads, blockIdx.x, threadIdx.x);
+}
+
+__global__ void __launch_bounds__(EHIC_LANE_BWD_GROUPS * EHIC_LANE_WARPS * 32, 1)
+backward_lane32_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, GatherArgs ga, int n_quads)
+{
+    const int group = threadIdx.x / (EHIC_LANE_WARPS * 32), tid = threadIdx.x % (EHIC_LANE_WARPS * 32);
+    long long v0, v1;
+    lane_resident_range(sc, v0, v1);
+    for (long long v = v0 + group; v < v1; v += EHIC_LANE_BWD_GROUPS) backward_lane32_body(dm, ld, ga, n_quads, v, tid);
 }
 
 // Combine + epilogue of the tile path: thread <-> (replica, structure, bead).

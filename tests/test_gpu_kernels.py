@@ -482,6 +482,35 @@ def test_lane_path_reversed_and_duplicate_pairs(co, monkeypatch):
     assert relerr(out["grad"][0], co.calculate_gradient(pb["X"], pb["alpha"], pb["norm"], cds, data)) < FAST_TOL
 
 
+@pytest.mark.parametrize("fp32", [False, True])
+def test_lane_replica_resident_launches_equal_the_plain_grid(monkeypatch, fp32):
+    """replica-resident launches (one CTA per SM walking a contiguous, work-balanced range of a replica's virtual
+    blocks so that its lane copy stays in L1) run the same bodies as the plain grid: results are identical bit for bit"""
+    import torch
+    pb = make_problem(seed=5, S=20, N=400, density=0.2, min_sep=2, step=0.8)
+    R, L = 24, 3
+    rng = np.random.default_rng(2)
+    X = np.stack([pb["X"] + rng.normal(scale=0.03, size=pb["X"].shape) for _ in range(R)]).reshape(R, -1)
+    P = rng.normal(size=X.shape)
+    norm = rng.uniform(1, 5, R); lam = np.linspace(0.1, 1.0, R); bet = np.linspace(1.0, 0.1, R); eps = np.full(R, 1e-3)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    monkeypatch.setenv("EHIC_PATH", "lanes")
+    monkeypatch.setenv("EHIC_TRAJ", "multi")
+    res = {}
+    for mode in ("0", "2"):
+        monkeypatch.setenv("EHIC_LANE_RESIDENT", mode)
+        m = _model(pb, False, max_replicas=R, fp32=fp32)
+        out = m.evaluate(X, norm, lam, bet, energies=True, md=True)
+        x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
+        m.hmc_trajectory_device(R, L, x_t, p_t, t(norm), t(lam), t(bet), t(eps), H_t)
+        torch.cuda.synchronize()
+        res[mode] = [out["grad"], out["md"], out["energies"], x_t.cpu().numpy(), p_t.cpu().numpy(), H_t.cpu().numpy()]
+        m.close()
+    for a, b in zip(res["0"], res["2"]):
+        assert np.isfinite(a).all() and np.array_equal(a, b)
+
+
 def test_lane_path_is_chosen_for_sparse_lists_with_enough_structures(monkeypatch):
     monkeypatch.delenv("EHIC_PATH", raising=False)
     assert _model(make_problem(seed=3, S=30, N=256, density=0.1), False).info()["path"] == "lanes"
@@ -685,21 +714,24 @@ def test_verlet_list_trajectory_equals_all_pairs_trajectory(monkeypatch, scenari
     dev = torch.device("cuda:0")
     t = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
     res = {}
-    for verlet in ("1", "0"):
-        monkeypatch.setenv("EHIC_VERLET", verlet)
+    for mode in ("fused", "kernels", "off"):             # one verlet_step_kernel per step / check + build + force kernels / all-pairs
+        monkeypatch.setenv("EHIC_VERLET", "0" if mode == "off" else "1")
+        monkeypatch.setenv("EHIC_VERLET_FUSED", "0" if mode == "kernels" else "1")
         m = _model(pb, False, max_replicas=R)
         x_t, p_t, H_t = t(X), t(P), torch.zeros(R, 4, dtype=torch.float64, device=dev)
         l0 = launch_count()
         for _ in range(2):                               # second trajectory starts from a list built in the first
             m.hmc_trajectory_device(R, L, x_t, p_t, t(norm), t(lam), t(bet), t(eps), H_t)
         torch.cuda.synchronize()
-        res[verlet] = (x_t.cpu().numpy(), p_t.cpu().numpy(), H_t.cpu().numpy(), launch_count() - l0)
+        res[mode] = (x_t.cpu().numpy(), p_t.cpu().numpy(), H_t.cpu().numpy(), launch_count() - l0)
         m.close()
-    assert res["1"][3] > res["0"][3]                      # the list kernels did run
-    assert relerr(res["1"][0], res["0"][0]) < 1e-12
-    assert relerr(res["1"][1], res["0"][1]) < 1e-10
-    np.testing.assert_allclose(res["1"][2], res["0"][2], rtol=1e-11)
-    assert np.all(np.isfinite(res["1"][2]))
+    assert res["kernels"][3] > res["off"][3] > res["fused"][3]      # the list kernels did run; the fused step is one launch
+    for mode in ("fused", "kernels"):
+        assert relerr(res[mode][0], res["off"][0]) < 1e-12
+        assert relerr(res[mode][1], res["off"][1]) < 1e-10
+        np.testing.assert_allclose(res[mode][2], res["off"][2], rtol=1e-11)
+        assert np.all(np.isfinite(res[mode][2]))
+    assert np.array_equal(res["fused"][0], res["kernels"][0])      # same lists, same order, same arithmetic
 
 
 def test_verlet_lists_survive_changing_batch_sizes(monkeypatch):
