@@ -479,10 +479,16 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
             if (cudaMemset(ip, 0, sizeof(int) * Rm * S * (size_t)(2 + dm.Np)) != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_CUDA, "cudaMemset failed"); }
             m->vl.state = ip; m->vl.stale = ip + Rm * S; m->vl.cnt = ip + 2 * Rm * S; m->vl.idx = reinterpret_cast<unsigned short *>(ip + Rm * S * (size_t)(2 + dm.Np + 32) / 32 * 32);     // 128-byte aligned
             DA(m->vl.xref, xs_n);
+            {
+                unsigned short *pp = nullptr;
+                if (cudaMalloc(&pp, sizeof(unsigned short) * Rm * S * (size_t)dm.Np) != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_NOMEM, "cudaMalloc failed"); }
+                m->owned.push_back(pp); m->vl.perm = pp;
+            }
             { const char *vf = getenv("EHIC_VERLET_FUSED"); m->vl_fused = !(vf && !strcmp(vf, "0")); }
-            const int vsm = (int)(sizeof(double) * 4 * (size_t)dm.Np);
+            const int vsm = (int)((sizeof(double) * 4 + sizeof(int)) * (size_t)dm.Np);
             cudaError_t ev = cudaFuncSetAttribute(verlet_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);
             if (ev == cudaSuccess) ev = cudaFuncSetAttribute(verlet_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);
+            if (ev == cudaSuccess) ev = cudaFuncSetAttribute(verlet_step_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);
             if (ev == cudaSuccess) ev = cudaFuncSetAttribute(verlet_step_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);
             if (ev == cudaSuccess) ev = cudaFuncSetAttribute(verlet_step_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);
             if (ev != cudaSuccess) { cudaGetLastError(); m->vl_fused = false; }
@@ -760,12 +766,13 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
         // one launch per step: displacement check, conditional list rebuild, list (or overflow all-pairs) force, backbone,
         // sphere and the energy sums of every structure (kernels.cuh: verlet_step_kernel)
         const unsigned n_struct = (unsigned)((long long)R * m->dm.S);
-        const size_t vsm = sizeof(double) * 4 * (size_t)m->dm.Np;
+        const size_t vsm = (sizeof(double) * 4 + sizeof(int)) * (size_t)m->dm.Np;
         double *pc = want_energy ? m->partC : nullptr;
         if (want_energy) CU(cudaMemsetAsync(m->partP, 0, sizeof(double) * 3 * (size_t)R * m->dm.S * m->nPx, st));   // nothing from prior_kernel
         const int N = m->dm.N;
         if (N <= 128) verlet_step_kernel<128><<<n_struct, 128, vsm, st>>>(m->dm, m->vl, xs, d_beta, gp, pc, terms);
         else if (N <= 256) verlet_step_kernel<256><<<n_struct, 256, vsm, st>>>(m->dm, m->vl, xs, d_beta, gp, pc, terms);
+        else if (N <= 320) verlet_step_kernel<320><<<n_struct, 320, vsm, st>>>(m->dm, m->vl, xs, d_beta, gp, pc, terms);
         else if (N <= 384) verlet_step_kernel<384><<<n_struct, 384, vsm, st>>>(m->dm, m->vl, xs, d_beta, gp, pc, terms);
         else verlet_step_kernel<512><<<n_struct, 512, vsm, st>>>(m->dm, m->vl, xs, d_beta, gp, pc, terms);
         LAUNCHED();
@@ -925,7 +932,7 @@ struct SlotShift {
             if (m->use_verlet) {
                 const size_t sS = z * (size_t)m->dm.S;
                 m->vl.state += sS; m->vl.stale += sS; m->vl.cnt += sS * m->dm.Np;
-                m->vl.idx += sS * (size_t)m->dm.Np * EHIC_VL_CAP; m->vl.xref += z * m->wss.xs;
+                m->vl.idx += sS * (size_t)m->dm.Np * EHIC_VL_CAP; m->vl.xref += z * m->wss.xs; m->vl.perm += sS * m->dm.Np;
             }
         }
         xs0 = m->xs[0]; xt0 = m->xt[0]; wbuf = m->wbuf; tw = m->tw; gprior = m->gprior; bbox = m->bbox; partC = m->partC;

@@ -481,7 +481,8 @@ __device__ __forceinline__ bool structure_fits_cells(const double *__restrict__ 
 // Backbone and sphere restraints of one bead (IEEE arithmetic and the reference's operation order in both
 // modes); adds to (g0, g1, g2) and accumulates the squared violations.  Shared by prior_kernel and
 // verlet_force_kernel.
-__device__ __forceinline__ void bonded_terms(const DevModel &dm, const double *__restrict__ xk, int Np, int b, bool bead_ok, int bb,
+template <class XAt>
+__device__ __forceinline__ void bonded_terms_t(const DevModel &dm, XAt xat, int b, bool bead_ok, int bb,
                                              double xb0, double xb1, double xb2, double rb, int terms,
                                              double &g0, double &g1, double &g2, double &e_bb, double &e_sp)
 {
@@ -492,7 +493,7 @@ __device__ __forceinline__ void bonded_terms(const DevModel &dm, const double *_
         double res0 = 0.0, res1 = 0.0, res2 = 0.0;
         if (has_prev) {   // i = b, i-1 = b-1
             const double ul = dm.bb_ul[b - 1], ll = dm.bb_ll[b - 1];
-            double d0 = __dsub_rn(xb0, xk[b - 1]), d1 = __dsub_rn(xb1, xk[Np + b - 1]), d2 = __dsub_rn(xb2, xk[2 * Np + b - 1]);
+            double d0 = __dsub_rn(xb0, xat(b - 1, 0)), d1 = __dsub_rn(xb1, xat(b - 1, 1)), d2 = __dsub_rn(xb2, xat(b - 1, 2));
             double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
             if (s > __dmul_rn(ul, ul)) {
                 double d = __dsqrt_rn(s), a = __dsub_rn(d, ul);
@@ -506,7 +507,7 @@ __device__ __forceinline__ void bonded_terms(const DevModel &dm, const double *_
         }
         if (has_next) {   // i = b+1, i-1 = b
             const double ul = dm.bb_ul[bb], ll = dm.bb_ll[bb];
-            double d0 = __dsub_rn(xk[b + 1], xb0), d1 = __dsub_rn(xk[Np + b + 1], xb1), d2 = __dsub_rn(xk[2 * Np + b + 1], xb2);
+            double d0 = __dsub_rn(xat(b + 1, 0), xb0), d1 = __dsub_rn(xat(b + 1, 1), xb1), d2 = __dsub_rn(xat(b + 1, 2), xb2);
             double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
             if (s > __dmul_rn(ul, ul)) {
                 double d = __dsqrt_rn(s), a = __dsub_rn(d, ul);
@@ -543,6 +544,22 @@ __device__ __forceinline__ void bonded_terms(const DevModel &dm, const double *_
         }
     }
 
+}
+
+// coordinates in the SoA working copy xk[3][Np]
+__device__ __forceinline__ void bonded_terms(const DevModel &dm, const double *__restrict__ xk, int Np, int b, bool bead_ok, int bb,
+                                             double xb0, double xb1, double xb2, double rb, int terms,
+                                             double &g0, double &g1, double &g2, double &e_bb, double &e_sp)
+{
+    bonded_terms_t(dm, [=](int o, int c) { return xk[c * Np + o]; }, b, bead_ok, bb, xb0, xb1, xb2, rb, terms, g0, g1, g2, e_bb, e_sp);
+}
+// coordinates as (x, y, z, radius) records (verlet_step_kernel's shared-memory copy)
+__device__ __forceinline__ void bonded_terms_rec(const DevModel &dm, const double4 *rec, int b,
+                                                 double xb0, double xb1, double xb2, double rb, int terms,
+                                                 double &g0, double &g1, double &g2, double &e_bb, double &e_sp)
+{
+    bonded_terms_t(dm, [=](int o, int c) { const double4 v = rec[o]; return c == 0 ? v.x : (c == 1 ? v.y : v.z); },
+                   b, true, b, xb0, xb1, xb2, rb, terms, g0, g1, g2, e_bb, e_sp);
 }
 
 template <bool EXACT, int EHIC_PRIOR_THREADS>
@@ -877,6 +894,7 @@ struct VerletDev {
     int *cnt;               // [R*S][Np]
     unsigned short *idx;    // [R*S][Np][EHIC_VL_CAP]: a bead's list is one 128-byte line (N < 4096 fits 16 bits)
     double *xref;           // [R*S][3][Np]
+    unsigned short *perm;   // [R*S][Np] force-phase work order of verlet_step_kernel: beads by list length, longest first
     double skin;
 };
 
@@ -1288,24 +1306,24 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
 // A thread reads back only list rows it wrote itself, so no grid-wide ordering is needed.  Energies: thread <-> bead
 // is static, the block sum has a fixed order.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 8 : THREADS <= 256 ? 4 : THREADS <= 320 ? 3 : 2)
 verlet_step_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, const double *__restrict__ beta,
                    double *__restrict__ gprior, double *__restrict__ partC, int terms)
 {
-    extern __shared__ __align__(16) double vsm[];              // [4][Np]: x, y, z, radius
+    extern __shared__ __align__(16) double vsm[];              // [Np] records (x, y, z, radius), then [Np] ints (list lengths)
     __shared__ double sh[3][THREADS / 32];
     const long long rk = blockIdx.x;
     const int r = (int)(rk / dm.S);
     const int Np = dm.Np, N = dm.N, tid = threadIdx.x;
     const double *xk = xs + rk * 3LL * Np;
-    double *sx = vsm, *srad = vsm + 3 * Np;
+    double4 *sb = reinterpret_cast<double4 *>(vsm);
+    int *s_cnt = reinterpret_cast<int *>(vsm + 4 * Np);
     int st = vl.state[rk];
     double *xr = vl.xref + rk * 3LL * Np;
     double mx = 0.0;
     for (int b = tid; b < Np; b += THREADS) {
         const double x0 = xk[b], x1 = xk[Np + b], x2 = xk[2 * Np + b];
-        sx[b] = x0; sx[Np + b] = x1; sx[2 * Np + b] = x2;
-        srad[b] = dm.radii[min(b, N - 1)];
+        sb[b] = make_double4(x0, x1, x2, dm.radii[min(b, N - 1)]);
         if (st == 1 && b < N) {
             const double d0 = x0 - xr[b], d1 = x1 - xr[Np + b], d2 = x2 - xr[2 * Np + b];
             const double d = fma(d2, d2, fma(d1, d1, d0 * d0));
@@ -1317,48 +1335,63 @@ verlet_step_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, con
     if (st != 1) __syncthreads();                                            // shared coordinates complete
     int *cnt = vl.cnt + rk * Np;
     unsigned short *idx = vl.idx + rk * (long long)Np * EHIC_VL_CAP;
+    unsigned short *perm = vl.perm + rk * Np;
     if (stale) {
         bool over = false;
         const double skin = vl.skin;
         for (int b = tid; b < N; b += THREADS) {
-            const double xb0 = sx[b], xb1 = sx[Np + b], xb2 = sx[2 * Np + b], rb = srad[b];
+            const double4 me = sb[b];
             unsigned short *row = idx + (long long)b * EHIC_VL_CAP;
             int n = 0;
             for (int o = 0; o < N; o++) {
-                const double dx = sx[o] - xb0, dy = sx[Np + o] - xb1, dz = sx[2 * Np + o] - xb2;
+                const double4 p = sb[o];
+                const double dx = p.x - me.x, dy = p.y - me.y, dz = p.z - me.z;
                 const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                const double lim = rb + srad[o] + skin;
+                const double lim = me.w + p.w + skin;
                 if (!(s2 >= lim * lim) && o != b) {             // !(>=): NaN distances are listed, like the sweep would see them
                     if (n < EHIC_VL_CAP) row[n] = (unsigned short)o;
                     n++;
                 }
             }
             cnt[b] = min(n, EHIC_VL_CAP);
+            s_cnt[b] = min(n, EHIC_VL_CAP);
             over = over || n > EHIC_VL_CAP;
-            xr[b] = xb0; xr[Np + b] = xb1; xr[2 * Np + b] = xb2;
+            xr[b] = me.x; xr[Np + b] = me.y; xr[2 * Np + b] = me.z;
         }
-        st = __syncthreads_or(over) ? 2 : 1;
+        st = __syncthreads_or(over) ? 2 : 1;                  // (also: s_cnt complete)
         if (tid == 0) vl.state[rk] = st;
+        // work order of the force phase: beads sorted by list length, longest first (the lanes of a warp then walk lists of
+        // similar length: a warp costs its longest list).  Rank by counting -- deterministic, O(N^2) once per rebuild.
+        for (int b = tid; b < N; b += THREADS) {
+            const int c = s_cnt[b];
+            int rank = 0;
+            for (int o = 0; o < N; o++) { const int co = s_cnt[o]; rank += (co > c || (co == c && o < b)) ? 1 : 0; }
+            perm[rank] = (unsigned short)b;
+        }
+        __syncthreads();                                        // perm is read by other threads below (same CTA)
     }
     const double sc = (beta ? beta[r] : 1.0) * (dm.k_nb * 2.0);
     double e_nb = 0.0, e_bb = 0.0, e_sp = 0.0;
-    for (int b = tid; b < N; b += THREADS) {
-        const double xb0 = sx[b], xb1 = sx[Np + b], xb2 = sx[2 * Np + b], rb = srad[b];
+    for (int t = tid; t < N; t += THREADS) {
+        const int b = st == 2 ? t : (int)perm[t];
+        const double4 me = sb[b];
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        auto visit = [&](int o) {
-            const double dx = sx[o] - xb0, dy = sx[Np + o] - xb1, dz = sx[2 * Np + o] - xb2;
+        auto visit = [&](int o, bool live) {
+            // branch-free: contacts are common inside compact structures, so a warp takes the contact arithmetic for
+            // nearly every visit anyway; a miss contributes through a = 0
+            const double4 p = sb[o];
+            const double dx = p.x - me.x, dy = p.y - me.y, dz = p.z - me.z;
             const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            const double d0 = rb + srad[o];
-            if (s2 < d0 * d0) {
-                const double rd = rsqrt_nr(s2);
-                const double a = d0 - s2 * rd, aa = a * a;
-                const double g = aa * a * rd;
-                a0 = fma(g, dx, a0); a1 = fma(g, dy, a1); a2 = fma(g, dz, a2);
-                e_nb += aa * aa;
-            }
+            const double d0 = me.w + p.w;
+            const double rd = rsqrt_nr(s2);
+            const bool hit = live && s2 < d0 * d0;
+            const double a = hit ? d0 - s2 * rd : 0.0, rdm = hit ? rd : 0.0, aa = a * a;
+            const double g = aa * a * rdm;
+            a0 = fma(g, dx, a0); a1 = fma(g, dy, a1); a2 = fma(g, dz, a2);
+            e_nb += aa * aa;
         };
         if (st == 2) {
-            for (int o = 0; o < N; o++) if (o != b) visit(o);
+            for (int o = 0; o < N; o++) visit(o == b ? (b + 1 < N ? b + 1 : b - 1) : o, o != b);
         } else {
             // ascending partner order, as in prior_kernel; the list of a bead is one 128-byte line, 8 indices per load
             const int n = cnt[b];
@@ -1367,12 +1400,15 @@ verlet_step_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, con
                 const uint4 w = row[u0 >> 3];
                 const unsigned ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (u0 + u < n) visit((int)((ws[u >> 1] >> (16 * (u & 1))) & 0xffffu));
+                for (int u = 0; u < 8; u++) {
+                    const bool live = u0 + u < n;
+                    if (u < 4 || u0 + 4 < n)                   // second half of a block only when the list reaches into it
+                        visit(live ? (int)((ws[u >> 1] >> (16 * (u & 1))) & 0xffffu) : (b > 0 ? b - 1 : 1), live);
+                }
             }
         }
         double g0 = sc * a0, g1 = sc * a1, g2 = sc * a2;
-        bonded_terms(dm, sx, Np, b, true, b, xb0, xb1, xb2, rb, terms, g0, g1, g2, e_bb, e_sp);
+        bonded_terms_rec(dm, sb, b, me.x, me.y, me.z, me.w, terms, g0, g1, g2, e_bb, e_sp);
         if (gprior) {
             double *o = gprior + (rk * N + b) * 3;
             o[0] = g0; o[1] = g1; o[2] = g2;
