@@ -1607,6 +1607,14 @@ forward_lane_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, const double
 }
 
 #define EHIC_LANE_WARPS 4
+#define EHIC_PRAGMA(x) _Pragma(#x)
+#define EHIC_UNROLL(n) EHIC_PRAGMA(unroll n)
+#ifndef EHIC_LANE_BWD_UNROLL
+#define EHIC_LANE_BWD_UNROLL 4
+#endif
+#ifndef EHIC_LANE_BWD_MIN_CTAS
+#define EHIC_LANE_BWD_MIN_CTAS 8      // 64 registers, 32 warps per SM: measured best of 5..9 CTAs x unroll 4 / 6 / 8 on nora2012 and config E
+#endif
 // Epilogue shared by the FP64 and FP32 backward lane kernels: lammda * g + priors, optional leapfrog kick + drift
 // (the drifted positions go to both working copies; F32: the lane copy holds (hi, lo) float pairs), kinetic partials.
 template <bool F32>
@@ -1657,7 +1665,8 @@ __device__ __forceinline__ void lane_epilogue(const DevModel &dm, const LaneDev 
 // consecutive beads of one structure group, so neighbouring rows share partner lines in L1.
 // Epilogue as in gather_kernel (lammda * g + priors, optional leapfrog kick + drift).
 __device__ __forceinline__ void
-backward_lane_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, int n_quads, long long vblock, int tid)
+backward_lane_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, int n_quads, long long vblock, int tid,
+                   int4 *stage_ent /* [EHIC_LANE_WARPS * 32] */, double *stage_w /* [EHIC_LANE_WARPS * 32] */)
 {
     const int lane = tid & 31, warp = tid >> 5;
     const int quad = (int)(vblock % n_quads);
@@ -1678,40 +1687,60 @@ backward_lane_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, 
         const long long e0 = ld.row_off[b], e1 = ld.row_off[b + 1];
         const double *wr = ga.wbuf + (long long)r * dm.wstride;
         const double alpha = dm.alpha;
-#pragma unroll 4
-        for (long long e = e0; e < e1; e++) {
-            const int4 v = __ldg(reinterpret_cast<const int4 *>(ld.ent + e));
-            const double dc = __hiloint2double(v.y, v.x);
-            const double w = wr[e];
-            const double *q = xk + (long long)v.z * 96;
-            const double dx = q[0] - x0, dy = q[32] - x1, dz = q[64] - x2;
-            const double s = fma(dz, dz, fma(dy, dy, dx * dx));
-            const double rd = rsqrt_nr(s);
-            const double tt = alpha * (dc - s * rd);
-            const double rq = rsqrt_nr(fma(tt, tt, 1.0));
-            const double f = w * ((rq * rq) * (rq * rd));
-            acc0 = fma(f, dx, acc0);
-            acc1 = fma(f, dy, acc1);
-            acc2 = fma(f, dz, acc2);
+        // The row's metadata travels in blocks of 32 entries: ONE coalesced load brings (dc, partner) and the weight of
+        // entry eb + lane, the block is parked in the warp's shared-memory slot and read back as broadcasts.  The
+        // partner index of every entry of the block is then known up front, so the coordinate loads of the next entries
+        // are not chained behind a metadata load each (that chain was 17 % of the kernel's stall samples), and the next
+        // block is requested while this one is worked on.
+        int4 *se = stage_ent + (tid >> 5) * 32;
+        double *sw = stage_w + (tid >> 5) * 32;
+        int4 nv = make_int4(0, 0, 0, 0); double nw = 0.0;
+        if (e0 < e1) { const long long e = min(e0 + lane, e1 - 1); nv = __ldg(reinterpret_cast<const int4 *>(ld.ent + e)); nw = wr[e]; }
+        for (long long eb = e0; eb < e1; eb += 32) {
+            __syncwarp();                                // everybody is done reading the previous block
+            se[lane] = nv; sw[lane] = nw;
+            __syncwarp();
+            if (eb + 32 < e1) { const long long e = min(eb + 32 + lane, e1 - 1); nv = __ldg(reinterpret_cast<const int4 *>(ld.ent + e)); nw = wr[e]; }
+            const int n = (int)min(32LL, e1 - eb);
+EHIC_UNROLL(EHIC_LANE_BWD_UNROLL)
+            for (int qe = 0; qe < n; qe++) {
+                const int4 v = se[qe];
+                const double dc = __hiloint2double(v.y, v.x);
+                const double w = sw[qe];
+                const double *q = xk + (long long)v.z * 96;
+                const double dx = q[0] - x0, dy = q[32] - x1, dz = q[64] - x2;
+                const double s = fma(dz, dz, fma(dy, dy, dx * dx));
+                const double rd = rsqrt_nr(s);
+                const double tt = alpha * (dc - s * rd);
+                const double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                const double f = w * ((rq * rq) * (rq * rd));
+                acc0 = fma(f, dx, acc0);
+                acc1 = fma(f, dy, acc1);
+                acc2 = fma(f, dz, acc2);
+            }
         }
     }
     lane_epilogue<false>(dm, ld, ga, vblock, r, kg, k, b, lane, warp, k_ok && bead_ok, gstride, x0, x1, x2, acc0, acc1, acc2);
 }
 
-__global__ void __launch_bounds__(EHIC_LANE_WARPS * 32)
+__global__ void __launch_bounds__(EHIC_LANE_WARPS * 32, EHIC_LANE_BWD_MIN_CTAS)
 backward_lane_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
 {
-    backward_lane_body(dm, ld, ga, n_quads, blockIdx.x, threadIdx.x);
+    __shared__ int4 s_ent[EHIC_LANE_WARPS * 32];
+    __shared__ double s_w[EHIC_LANE_WARPS * 32];
+    backward_lane_body(dm, ld, ga, n_quads, blockIdx.x, threadIdx.x, s_ent, s_w);
 }
 
 #define EHIC_LANE_BWD_GROUPS 8                   // resident launch: 8 x 128 threads per SM
 __global__ void __launch_bounds__(EHIC_LANE_BWD_GROUPS * EHIC_LANE_WARPS * 32, 1)
 backward_lane_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, GatherArgs ga, int n_quads)
 {
+    __shared__ int4 s_ent[EHIC_LANE_BWD_GROUPS][EHIC_LANE_WARPS * 32];
+    __shared__ double s_w[EHIC_LANE_BWD_GROUPS][EHIC_LANE_WARPS * 32];
     const int group = threadIdx.x / (EHIC_LANE_WARPS * 32), tid = threadIdx.x % (EHIC_LANE_WARPS * 32);
     long long v0, v1;
     lane_resident_range(sc, v0, v1);
-    for (long long v = v0 + group; v < v1; v += EHIC_LANE_BWD_GROUPS) backward_lane_body(dm, ld, ga, n_quads, v, tid);
+    for (long long v = v0 + group; v < v1; v += EHIC_LANE_BWD_GROUPS) backward_lane_body(dm, ld, ga, n_quads, v, tid, s_ent[group], s_w[group]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -2439,7 +2468,7 @@ backward_tile32_kernel(DevModel dm, TileDev td, BackwardTile32Args ba)
 // summation structure as forward_lane_kernel / backward_lane_kernel; the pair arithmetic runs on the FP32 pipe
 // with the same safeguards as the FP32 tile kernels: the lane copy xg holds (hi, lo) float pairs and differences
 // are (hi - hi) + (lo - lo); the contact function of far-apart pairs avoids the 1 + t/q cancellation; per-pair sums
-// over the ensemble stay in FP32 (S terms); the force accumulators of a bead are flushed into FP64 every 64 row
+// over the ensemble stay in FP32 (S terms); the force accumulators of a bead are flushed into FP64 every 32 row
 // entries.  Contact distances come from float copies of the two list views, weights travel as floats in the
 // weight buffer; mock counts, Poisson weights, energies, priors and the leapfrog update stay FP64.
 __device__ __forceinline__ void
@@ -2550,7 +2579,8 @@ forward_lane32_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, const doub
 }
 
 __device__ __forceinline__ void
-backward_lane32_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, int n_quads, long long vblock, int tid)
+backward_lane32_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, int n_quads, long long vblock, int tid,
+                     int4 *stage_ent /* [EHIC_LANE_WARPS * 32] */)
 {
     const int lane = tid & 31, warp = tid >> 5;
     const int quad = (int)(vblock % n_quads);
@@ -2571,13 +2601,29 @@ backward_lane32_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga
         const float *wr = reinterpret_cast<const float *>(ga.wbuf) + (long long)r * dm.wstride * 2;
         const float alpha = (float)dm.alpha;
         float f0 = 0.f, f1 = 0.f, f2 = 0.f;
-        for (long long eb = e0; eb < e1; eb += 64) {    // FP32 partial sums of at most 64 entries
-            const long long ee = min(eb + 64, e1);
+        // metadata in blocks of 32 entries through the warp's shared-memory slot, as in backward_lane_body
+        int4 *se = stage_ent + (tid >> 5) * 32;
+        int4 nv = make_int4(0, 0, 0, 0);
+        if (e0 < e1) {
+            const long long e = min(e0 + lane, e1 - 1);
+            const int2 t = __ldg(reinterpret_cast<const int2 *>(ld.ent32 + e));
+            nv = make_int4(t.x, t.y, __float_as_int(wr[e]), 0);
+        }
+        for (long long eb = e0; eb < e1; eb += 32) {    // FP32 partial sums of at most 32 entries
+            __syncwarp();
+            se[lane] = nv;
+            __syncwarp();
+            if (eb + 32 < e1) {
+                const long long e = min(eb + 32 + lane, e1 - 1);
+                const int2 t = __ldg(reinterpret_cast<const int2 *>(ld.ent32 + e));
+                nv = make_int4(t.x, t.y, __float_as_int(wr[e]), 0);
+            }
+            const int n = (int)min(32LL, e1 - eb);
 #pragma unroll 4
-            for (long long e = eb; e < ee; e++) {
-                const int2 v = __ldg(reinterpret_cast<const int2 *>(ld.ent32 + e));
+            for (int qe = 0; qe < n; qe++) {
+                const int4 v = se[qe];
                 const float dc = __int_as_float(v.x);
-                const float w = wr[e];
+                const float w = __int_as_float(v.z);
                 const float2 *q = xk + (long long)v.y * 96;
                 const float2 q0 = q[0], q1 = q[32], q2 = q[64];
                 const float dx = (q0.x - x0.x) + (q0.y - x0.y);
@@ -2601,7 +2647,8 @@ backward_lane32_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga
 __global__ void __launch_bounds__(EHIC_LANE_WARPS * 32)
 backward_lane32_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
 {
-    backward_lane32_body(dm, ld, ga, n_quads, blockIdx.x, threadIdx.x);
+    __shared__ int4 s_ent[EHIC_LANE_WARPS * 32];
+    backward_lane32_body(dm, ld, ga, n_quads, blockIdx.x, threadIdx.x, s_ent);
 }
 
 __global__ void __launch_bounds__(EHIC_LANE_BWD_GROUPS * EHIC_LANE_WARPS * 32, 1)
@@ -2610,7 +2657,8 @@ backward_lane32_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, GatherArg
     const int group = threadIdx.x / (EHIC_LANE_WARPS * 32), tid = threadIdx.x % (EHIC_LANE_WARPS * 32);
     long long v0, v1;
     lane_resident_range(sc, v0, v1);
-    for (long long v = v0 + group; v < v1; v += EHIC_LANE_BWD_GROUPS) backward_lane32_body(dm, ld, ga, n_quads, v, tid);
+    __shared__ int4 s_ent[EHIC_LANE_BWD_GROUPS][EHIC_LANE_WARPS * 32];
+    for (long long v = v0 + group; v < v1; v += EHIC_LANE_BWD_GROUPS) backward_lane32_body(dm, ld, ga, n_quads, v, tid, s_ent[group]);
 }
 
 // Combine + epilogue of the tile path: thread <-> (replica, structure, bead).
