@@ -61,6 +61,11 @@ struct ehic_model {
     bool use_lanes = false;         // sparse list + fast mode + enough structures to fill warps: lane path
     LaneDev ld{};
     int n_quads = 0;                // lane path: backward CTAs per (replica, structure group)
+    int n_quads_split = 0;          // the same with long rows cut into segments (few replicas per GPU)
+    const int4 *lane_items_split = nullptr;
+    int last_lane_quads = 0;        // quads per (replica, structure group) of the last backward launch (kinetic partials)
+    int lane_split_mode = -1;       // EHIC_LANE_SPLIT: 0 / 1 forced, -1 by launch size
+    std::vector<long long> lane_item_work;  // host: CSR entries (+ epilogue) per backward work item
     const long long *lane_cum = nullptr;   // [nkg * n_quads + 1] cumulative CSR entries of a replica's backward virtual blocks
     bool lane_res_fwd = false, lane_res_bwd = false;   // replica-resident launches (a replica's lane copy fits one SM's L1)
     int n_sm = 0;
@@ -390,7 +395,44 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
 #undef UPL
             m->use_lanes = want;
             m->tc_possible = tc_want;
-            m->n_quads = (N + EHIC_LANE_WARPS - 1) / EHIC_LANE_WARPS;
+            // backward work items: one warp each, four to a CTA; two lists.  The plain one gives every bead one warp
+            // (neighbouring rows then share partner lines in L1).  In the SPLIT one rows are cut into 2 or 4 segments that
+            // sit in the same CTA and are combined in shared memory: when a GPU holds few replicas of a medium system --
+            // the ladder strong-scaled over 8 GPUs -- the launch is as long as the serial walk of the longest row, and
+            // splitting shortens it (nora2012 backward pass, 19 replicas: 0.066 -> 0.051 ms, 38: 0.095 -> 0.088); with many
+            // replicas the extra CTAs and barriers cost 12 %, so launch_gather picks the list by the size of the launch.
+            // EHIC_LANE_SPLIT=0/1 forces one of them.
+            {
+                const char *sp = getenv("EHIC_LANE_SPLIT");
+                m->lane_split_mode = sp ? (atoi(sp) != 0 ? 1 : 0) : -1;
+                for (int pass = 0; pass < 2; pass++) {
+                    const bool split = pass == 1;
+                    std::vector<int4> items;
+                    const int4 none = make_int4(-1, 0, 0, 0 | (1 << 8));
+                    for (int it = 0; it < N; it++) {
+                        const int b = order[it];
+                        const int len = (int)L.row_len[b];
+                        const int nseg = !split ? 1 : (len > 96 ? 4 : (len > 48 ? 2 : 1));
+                        while ((int)(items.size() % EHIC_LANE_WARPS) + nseg > EHIC_LANE_WARPS) {
+                            int4 e = none; e.w = (int)(items.size() % EHIC_LANE_WARPS) | (1 << 8); items.push_back(e);
+                        }
+                        const int lead = (int)(items.size() % EHIC_LANE_WARPS);
+                        for (int sgm = 0; sgm < nseg; sgm++)
+                            items.push_back(make_int4(b, (int)(roff[b] + (long long)len * sgm / nseg),
+                                                      (int)(roff[b] + (long long)len * (sgm + 1) / nseg), lead | (nseg << 8)));
+                    }
+                    while (items.size() % EHIC_LANE_WARPS) { int4 e = none; e.w = (int)(items.size() % EHIC_LANE_WARPS) | (1 << 8); items.push_back(e); }
+                    if (!split) {
+                        m->n_quads = (int)(items.size() / EHIC_LANE_WARPS);
+                        rc = upload(m, items, &m->ld.items); if (rc) { ehic_model_destroy(m); return rc; }
+                        m->lane_item_work.assign(items.size(), 0);
+                        for (size_t q = 0; q < items.size(); q++) m->lane_item_work[q] = (items[q].z - items[q].y) + (items[q].x >= 0 ? 8 : 0);
+                    } else {
+                        m->n_quads_split = (int)(items.size() / EHIC_LANE_WARPS);
+                        rc = upload(m, items, &m->lane_items_split); if (rc) { ehic_model_destroy(m); return rc; }
+                    }
+                }
+            }
             if (want) {
                 // replica-resident launches (kernels.cuh, lane_resident_range): chosen when the lane copy a pass walks --
                 // one structure group in the backward pass, all of them in the forward pass -- fits one SM's L1
@@ -399,10 +441,7 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
                 for (int kgq = 0; kgq < nkg; kgq++)
                     for (int q = 0; q < m->n_quads; q++) {
                         long long w = 0;
-                        for (int u = 0; u < EHIC_LANE_WARPS; u++) {
-                            const int it = q * EHIC_LANE_WARPS + u;
-                            if (it < N) w += L.row_len[order[it]] + 8;          // + the bead's epilogue
-                        }
+                        for (int u = 0; u < EHIC_LANE_WARPS; u++) w += m->lane_item_work[(size_t)q * EHIC_LANE_WARPS + u];   // entries + the bead's epilogue
                         cum[(size_t)kgq * m->n_quads + q + 1] = cum[(size_t)kgq * m->n_quads + q] + w;
                     }
                 rc = upload(m, cum, &m->lane_cum); if (rc) { ehic_model_destroy(m); return rc; }
@@ -496,14 +535,14 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
     }
     DA(m->partA, Rm * (size_t)std::max(m->nA, 1));
     DA(m->partP, Rm * (size_t)S * m->nPx * 3);
-    DA(m->partK, Rm * std::max((size_t)L.n_slices * m->nktg * m->gw, (size_t)m->n_quads * EHIC_LANE_WARPS * m->nkt));
+    DA(m->partK, Rm * std::max((size_t)L.n_slices * m->nktg * m->gw, (size_t)std::max(m->n_quads, m->n_quads_split) * EHIC_LANE_WARPS * m->nkt));
     DA(m->energies, Rm * 4); DA(m->kinetic, Rm);
     {
         auto &w = m->wss;
         w.xs = (size_t)S * 3 * dm.Np; w.xt = (size_t)m->nkt * dm.Np * m->kt * 3; w.wbuf = (size_t)dm.wstride;
         w.gprior = (size_t)S * N * 3; w.bbox = (size_t)S * L.n_slices * 6; w.partC = (size_t)S * 3; w.cell = (size_t)S * N;
         w.partA = (size_t)std::max(m->nA, 1); w.partP = (size_t)S * m->nPx * 3;
-        w.partK = std::max((size_t)L.n_slices * m->nktg * m->gw, (size_t)m->n_quads * EHIC_LANE_WARPS * m->nkt);
+        w.partK = std::max((size_t)L.n_slices * m->nktg * m->gw, (size_t)std::max(m->n_quads, m->n_quads_split) * EHIC_LANE_WARPS * m->nkt);
     }
     if (m->use_tiles) {
         m->nA_tile = m->td.n_tiles;                                   // one forward CTA (partial) per tile
@@ -879,14 +918,21 @@ static int launch_gather(ehic_model *m, const GatherArgs &ga, int R, cudaStream_
     }
     KernelTimer kt_(m, KC_GATHER, st);
     if (m->use_lanes) {
-        const unsigned blocks = (unsigned)((long long)R * m->ld.nkg * m->n_quads);
-        if (m->lane_res_bwd && (long long)blocks >= 2LL * EHIC_LANE_BWD_GROUPS * m->n_sm) {
+        // few replicas of a medium system: the split work list (long rows over 2 or 4 warps of a CTA)
+        const bool split = m->lane_split_mode >= 0 ? m->lane_split_mode == 1
+                                                   : (2 * m->dm.M <= 200000 && (long long)R * m->ld.nkg * m->n_quads < 3LL * 8 * m->n_sm);
+        LaneDev ldv = m->ld;
+        const int nq = split ? m->n_quads_split : m->n_quads;
+        if (split) ldv.items = m->lane_items_split;
+        const unsigned blocks = (unsigned)((long long)R * m->ld.nkg * nq);
+        if (!split && m->lane_res_bwd && (long long)blocks >= 2LL * EHIC_LANE_BWD_GROUPS * m->n_sm) {
             LaneSched sc{EHIC_LANE_BWD_GROUPS, (long long)blocks, m->ld.nkg * m->n_quads, m->lane_cum};
             const int th = EHIC_LANE_BWD_GROUPS * EHIC_LANE_WARPS * 32;
             if (m->f32) backward_lane32_resident_kernel<<<m->n_sm, th, 0, st>>>(m->dm, m->ld, sc, ga, m->n_quads);
             else backward_lane_resident_kernel<<<m->n_sm, th, 0, st>>>(m->dm, m->ld, sc, ga, m->n_quads);
-        } else if (m->f32) backward_lane32_kernel<<<blocks, EHIC_LANE_WARPS * 32, 0, st>>>(m->dm, m->ld, ga, m->n_quads);
-        else backward_lane_kernel<<<blocks, EHIC_LANE_WARPS * 32, 0, st>>>(m->dm, m->ld, ga, m->n_quads);
+        } else if (m->f32) backward_lane32_kernel<<<blocks, EHIC_LANE_WARPS * 32, 0, st>>>(m->dm, ldv, ga, nq);
+        else backward_lane_kernel<<<blocks, EHIC_LANE_WARPS * 32, 0, st>>>(m->dm, ldv, ga, nq);
+        m->last_lane_quads = nq;
         LAUNCHED();
         CU(cudaGetLastError());
         return EHIC_OK;
@@ -905,7 +951,7 @@ static int launch_finalize(ehic_model *m, int R, bool haveA, bool haveP, bool ha
                                        haveP ? m->partP : nullptr, (long long)m->dm.S * m->nPx,
                                        haveK ? m->partK : nullptr,
                                        m->use_tiles ? (long long)m->dm.S * m->nKc
-                                       : m->use_lanes ? (long long)m->ld.nkg * m->n_quads * EHIC_LANE_WARPS
+                                       : m->use_lanes ? (long long)m->ld.nkg * (m->last_lane_quads ? m->last_lane_quads : m->n_quads) * EHIC_LANE_WARPS
                                                       : (long long)m->dm.n_slices * m->nktg * m->gw,
                                        (haveP && m->last_prior_used_cells) ? m->partC : nullptr, m->dm.S,
                                        d_energies, d_kin);

@@ -1451,7 +1451,10 @@ struct LaneDev {
     const int *slot_a, *slot_b;     // [M]  CSR positions of (i -> j) and (j -> i)
     const long long *row_off;       // [N+1] CSR: both directions of every pair
     const LaneEnt *ent;             // [2M]
-    const int *order;               // [N] bead handled by backward work item q: identity, or longest rows first for ragged lists
+    const int *order;               // [N] beads in work order: identity, or longest rows first for ragged lists (cluster trajectory kernel)
+    const int4 *items;              // [4 n_quads] backward work items (bead or -1, first entry, end entry, lead | n_seg << 8):
+                                    // one warp each; the rows of medium systems are split into up to 4 segments that sit in the
+                                    // same quad (lead = warp of the first segment), so that a long row is not one warp's serial walk
     const LanePair32 *pairs32;      // [M]  FP32 mode only
     const LaneEnt32 *ent32;         // [2M] FP32 mode only
 };
@@ -1658,6 +1661,20 @@ __device__ __forceinline__ void lane_epilogue(const DevModel &dm, const LaneDev 
     }
 }
 
+// Segments of one bead within a quad: the partial forces go through shared memory and are added by the leader warp in
+// segment order (deterministic).  Returns whether this warp finishes the bead.
+__device__ __forceinline__ bool lane_combine_segments(double (*part)[3][32] /* [EHIC_LANE_WARPS] */, int group, int warp, int lane,
+                                                      int lead, int nseg, double &acc0, double &acc1, double &acc2)
+{
+    if (nseg > 1) { part[warp][0][lane] = acc0; part[warp][1][lane] = acc1; part[warp][2][lane] = acc2; }
+    group_sync(group, EHIC_LANE_WARPS * 32);
+    if (nseg > 1 && warp == lead) {
+        acc0 = part[lead][0][lane]; acc1 = part[lead][1][lane]; acc2 = part[lead][2][lane];
+        for (int q = 1; q < nseg; q++) { acc0 += part[lead + q][0][lane]; acc1 += part[lead + q][1][lane]; acc2 += part[lead + q][2][lane]; }
+    }
+    return warp == lead;
+}
+
 // Backward, lane form: warp <-> (replica, structure group, bead b); lane <-> structure.  The warp
 // walks the CSR row of b -- (partner, contact distance) and the weight are broadcast loads, the
 // partner's coordinates three coalesced rows -- and accumulates g_b of its 32 structures in
@@ -1665,17 +1682,18 @@ __device__ __forceinline__ void lane_epilogue(const DevModel &dm, const LaneDev 
 // consecutive beads of one structure group, so neighbouring rows share partner lines in L1.
 // Epilogue as in gather_kernel (lammda * g + priors, optional leapfrog kick + drift).
 __device__ __forceinline__ void
-backward_lane_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, int n_quads, long long vblock, int tid,
-                   int4 *stage_ent /* [EHIC_LANE_WARPS * 32] */, double *stage_w /* [EHIC_LANE_WARPS * 32] */)
+backward_lane_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, int n_quads, long long vblock, int tid, int group,
+                   int4 *stage_ent /* [EHIC_LANE_WARPS * 32] */, double *stage_w /* [EHIC_LANE_WARPS * 32] */,
+                   double (*part)[3][32] /* [EHIC_LANE_WARPS] */)
 {
     const int lane = tid & 31, warp = tid >> 5;
     const int quad = (int)(vblock % n_quads);
     const int tmp = (int)(vblock / n_quads);
     const int kg = tmp % ld.nkg;
     const int r = tmp / ld.nkg;
-    const int item = quad * EHIC_LANE_WARPS + warp;
-    const bool bead_ok = item < dm.N;
-    const int b = bead_ok ? ld.order[item] : dm.N - 1;
+    const int4 item = __ldg(ld.items + quad * EHIC_LANE_WARPS + warp);
+    const bool bead_ok = item.x >= 0;
+    const int b = bead_ok ? item.x : dm.N - 1;
     const int bb = b;
     const int k = kg * 32 + lane;
     const bool k_ok = k < dm.S;
@@ -1684,7 +1702,7 @@ backward_lane_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, 
     const double x0 = xk[(long long)bb * 96], x1 = xk[(long long)bb * 96 + 32], x2 = xk[(long long)bb * 96 + 64];
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
     if (ga.contact && dm.M > 0 && bead_ok) {            // warp-uniform
-        const long long e0 = ld.row_off[b], e1 = ld.row_off[b + 1];
+        const long long e0 = item.y, e1 = item.z;        // this warp's segment of the bead's CSR row
         const double *wr = ga.wbuf + (long long)r * dm.wstride;
         const double alpha = dm.alpha;
         // The row's metadata travels in blocks of 32 entries: ONE coalesced load brings (dc, partner) and the weight of
@@ -1720,7 +1738,8 @@ EHIC_UNROLL(EHIC_LANE_BWD_UNROLL)
             }
         }
     }
-    lane_epilogue<false>(dm, ld, ga, vblock, r, kg, k, b, lane, warp, k_ok && bead_ok, gstride, x0, x1, x2, acc0, acc1, acc2);
+    const bool leader = lane_combine_segments(part, group, warp, lane, item.w & 255, item.w >> 8, acc0, acc1, acc2);
+    lane_epilogue<false>(dm, ld, ga, vblock, r, kg, k, b, lane, warp, k_ok && bead_ok && leader, gstride, x0, x1, x2, acc0, acc1, acc2);
 }
 
 __global__ void __launch_bounds__(EHIC_LANE_WARPS * 32, EHIC_LANE_BWD_MIN_CTAS)
@@ -1728,7 +1747,8 @@ backward_lane_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
 {
     __shared__ int4 s_ent[EHIC_LANE_WARPS * 32];
     __shared__ double s_w[EHIC_LANE_WARPS * 32];
-    backward_lane_body(dm, ld, ga, n_quads, blockIdx.x, threadIdx.x, s_ent, s_w);
+    __shared__ double s_part[EHIC_LANE_WARPS][3][32];
+    backward_lane_body(dm, ld, ga, n_quads, blockIdx.x, threadIdx.x, 0, s_ent, s_w, s_part);
 }
 
 #define EHIC_LANE_BWD_GROUPS 8                   // resident launch: 8 x 128 threads per SM
@@ -1740,7 +1760,11 @@ backward_lane_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, GatherArgs 
     const int group = threadIdx.x / (EHIC_LANE_WARPS * 32), tid = threadIdx.x % (EHIC_LANE_WARPS * 32);
     long long v0, v1;
     lane_resident_range(sc, v0, v1);
-    for (long long v = v0 + group; v < v1; v += EHIC_LANE_BWD_GROUPS) backward_lane_body(dm, ld, ga, n_quads, v, tid, s_ent[group], s_w[group]);
+    __shared__ double s_part[EHIC_LANE_BWD_GROUPS][EHIC_LANE_WARPS][3][32];
+    for (long long v = v0 + group; v < v1; v += EHIC_LANE_BWD_GROUPS) {
+        backward_lane_body(dm, ld, ga, n_quads, v, tid, group, s_ent[group], s_w[group], s_part[group]);
+        group_sync(group, EHIC_LANE_WARPS * 32);         // the leader has read the partials before the group's next block overwrites them
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -2579,17 +2603,17 @@ forward_lane32_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, const doub
 }
 
 __device__ __forceinline__ void
-backward_lane32_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, int n_quads, long long vblock, int tid,
-                     int4 *stage_ent /* [EHIC_LANE_WARPS * 32] */)
+backward_lane32_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga, int n_quads, long long vblock, int tid, int group,
+                     int4 *stage_ent /* [EHIC_LANE_WARPS * 32] */, double (*part)[3][32] /* [EHIC_LANE_WARPS] */)
 {
     const int lane = tid & 31, warp = tid >> 5;
     const int quad = (int)(vblock % n_quads);
     const int tmp = (int)(vblock / n_quads);
     const int kg = tmp % ld.nkg;
     const int r = tmp / ld.nkg;
-    const int item = quad * EHIC_LANE_WARPS + warp;
-    const bool bead_ok = item < dm.N;
-    const int b = bead_ok ? ld.order[item] : dm.N - 1;
+    const int4 item = __ldg(ld.items + quad * EHIC_LANE_WARPS + warp);
+    const bool bead_ok = item.x >= 0;
+    const int b = bead_ok ? item.x : dm.N - 1;
     const int k = kg * 32 + lane;
     const bool k_ok = k < dm.S;
     const long long gstride = (long long)dm.Np * 96;
@@ -2597,7 +2621,7 @@ backward_lane32_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga
     const float2 x0 = xk[(long long)b * 96], x1 = xk[(long long)b * 96 + 32], x2 = xk[(long long)b * 96 + 64];
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
     if (ga.contact && dm.M > 0 && bead_ok) {            // warp-uniform
-        const long long e0 = ld.row_off[b], e1 = ld.row_off[b + 1];
+        const long long e0 = item.y, e1 = item.z;        // this warp's segment of the bead's CSR row
         const float *wr = reinterpret_cast<const float *>(ga.wbuf) + (long long)r * dm.wstride * 2;
         const float alpha = (float)dm.alpha;
         float f0 = 0.f, f1 = 0.f, f2 = 0.f;
@@ -2641,14 +2665,16 @@ backward_lane32_body(const DevModel &dm, const LaneDev &ld, const GatherArgs &ga
         }
     }
     // positions for the drift come from the FP64 SoA copy inside the epilogue
-    lane_epilogue<true>(dm, ld, ga, vblock, r, kg, k, b, lane, warp, k_ok && bead_ok, gstride, 0.0, 0.0, 0.0, acc0, acc1, acc2);
+    const bool leader = lane_combine_segments(part, group, warp, lane, item.w & 255, item.w >> 8, acc0, acc1, acc2);
+    lane_epilogue<true>(dm, ld, ga, vblock, r, kg, k, b, lane, warp, k_ok && bead_ok && leader, gstride, 0.0, 0.0, 0.0, acc0, acc1, acc2);
 }
 
 __global__ void __launch_bounds__(EHIC_LANE_WARPS * 32)
 backward_lane32_kernel(DevModel dm, LaneDev ld, GatherArgs ga, int n_quads)
 {
     __shared__ int4 s_ent[EHIC_LANE_WARPS * 32];
-    backward_lane32_body(dm, ld, ga, n_quads, blockIdx.x, threadIdx.x, s_ent);
+    __shared__ double s_part[EHIC_LANE_WARPS][3][32];
+    backward_lane32_body(dm, ld, ga, n_quads, blockIdx.x, threadIdx.x, 0, s_ent, s_part);
 }
 
 __global__ void __launch_bounds__(EHIC_LANE_BWD_GROUPS * EHIC_LANE_WARPS * 32, 1)
@@ -2658,7 +2684,11 @@ backward_lane32_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, GatherArg
     long long v0, v1;
     lane_resident_range(sc, v0, v1);
     __shared__ int4 s_ent[EHIC_LANE_BWD_GROUPS][EHIC_LANE_WARPS * 32];
-    for (long long v = v0 + group; v < v1; v += EHIC_LANE_BWD_GROUPS) backward_lane32_body(dm, ld, ga, n_quads, v, tid, s_ent[group]);
+    __shared__ double s_part[EHIC_LANE_BWD_GROUPS][EHIC_LANE_WARPS][3][32];
+    for (long long v = v0 + group; v < v1; v += EHIC_LANE_BWD_GROUPS) {
+        backward_lane32_body(dm, ld, ga, n_quads, v, tid, group, s_ent[group], s_part[group]);
+        group_sync(group, EHIC_LANE_WARPS * 32);
+    }
 }
 
 // Combine + epilogue of the tile path: thread <-> (replica, structure, bead).

@@ -497,6 +497,7 @@ def test_lane_replica_resident_launches_equal_the_plain_grid(monkeypatch, fp32):
     t = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
     monkeypatch.setenv("EHIC_PATH", "lanes")
     monkeypatch.setenv("EHIC_TRAJ", "multi")
+    monkeypatch.setenv("EHIC_LANE_SPLIT", "0")           # the resident backward launch walks the plain work list
     res = {}
     for mode in ("0", "2"):
         monkeypatch.setenv("EHIC_LANE_RESIDENT", mode)
@@ -509,6 +510,33 @@ def test_lane_replica_resident_launches_equal_the_plain_grid(monkeypatch, fp32):
         m.close()
     for a, b in zip(res["0"], res["2"]):
         assert np.isfinite(a).all() and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("fp32", [False, True])
+def test_lane_split_rows_equal_whole_rows(co, monkeypatch, fp32):
+    """backward lane kernels: long rows cut into 2 or 4 segments over the warps of a CTA (the work list of launches with
+    few replicas) against one warp per bead -- same terms, partial sums combined in segment order"""
+    pb = make_problem(seed=8, S=30, N=260, density=0.5, min_sep=1, step=0.8)       # rows of ~130 entries: 4 segments
+    R = 3
+    rng = np.random.default_rng(2)
+    X = np.stack([pb["X"] + rng.normal(scale=0.03, size=pb["X"].shape) for _ in range(R)]).reshape(R, -1)
+    norm = rng.uniform(1, 5, R); lam = np.array([0.2, 1.0, 0.6]); bet = np.array([1.0, 0.3, 0.0])
+    monkeypatch.setenv("EHIC_PATH", "lanes")
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("EHIC_LANE_SPLIT", mode)
+        m = _model(pb, False, max_replicas=R, fp32=fp32)
+        res[mode] = m.evaluate(X, norm, lam, bet, energies=True)
+        m.close()
+    assert not np.array_equal(res["0"]["grad"], res["1"]["grad"])                  # a different summation order
+    assert relerr(res["1"]["grad"], res["0"]["grad"]) < (1e-6 if fp32 else 1e-13)
+    np.testing.assert_array_equal(res["1"]["energies"], res["0"]["energies"])
+    g = co.calculate_gradient(X[0].reshape(pb["X"].shape), pb["alpha"], norm[0], pb["cds"], pb["data"])
+    monkeypatch.setenv("EHIC_LANE_SPLIT", "1")
+    m = _model(pb, False, max_replicas=R, fp32=fp32)
+    glik = m.evaluate(X[0], norm[0], terms=1)["grad"][0]
+    assert relerr(glik, g) < (FP32_TOL if fp32 else 1e-12)
+    m.close()
 
 
 def test_lane_path_is_chosen_for_sparse_lists_with_enough_structures(monkeypatch):
