@@ -92,7 +92,7 @@ struct ehic_model {
     std::vector<TcPlan> tc_plans;   // per batch size R
     bool tc_attr[4] = {false, false, false, false};
     bool use_verlet = false;        // HMC trajectories: nonbonded term from Verlet lists reused across leapfrog steps
-    bool vl_fused = true;           // one verlet_step_kernel per leapfrog step (EHIC_VERLET_FUSED=0: check / build / sweep / force kernels)
+    bool vl_fused = true;           // one verlet_step_kernel per leapfrog step (N <= 512); else check / build / sweep / force kernels
     VerletDev vl{};
     double *partA = nullptr, *partP = nullptr, *partK = nullptr;
     double *energies = nullptr, *kinetic = nullptr;
@@ -508,9 +508,18 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
                         !(ve && !strcmp(ve, "0")) &&
                         idx_bytes <= ((size_t)8 << 30);
         if (m->use_verlet) {
+            // One verlet_step_kernel per leapfrog step for structures of up to 512 beads, where the CTA's own all-pairs rebuild
+            // from shared memory is cheap; longer chains keep the check / build / force kernels, whose rebuild is pruned by
+            // the slice boxes and spread over many CTAs (config D at step sizes that make lists go stale every few steps:
+            // prior part 0.40 ms per leapfrog step with the kernel chain, 1.38 ms fused).  EHIC_VERLET_FUSED=0/1 overrides.
+            { const char *vf = getenv("EHIC_VERLET_FUSED"); m->vl_fused = vf ? strcmp(vf, "0") != 0 : N <= 512; }
+            // skin: the fused kernel pays ~6 normal steps for a rebuild, so it wants rarer rebuilds and accepts longer lists
+            // (nora2012 at its adapted step size 2.5e-3: 1.266 ms per step at 0.25 r_max, 1.129 at 0.7, 1.117 at 1.0); the
+            // kernel chain was tuned at 0.25 r_max in round 1
             const char *sk = getenv("EHIC_VERLET_SKIN");
-            m->vl.skin = (sk ? atof(sk) : 0.25) * m->r_max;
-            if (!(m->vl.skin > 0.0)) m->vl.skin = 0.25 * m->r_max;
+            const double skin_default = m->vl_fused ? 0.7 : 0.25;
+            m->vl.skin = (sk ? atof(sk) : skin_default) * m->r_max;
+            if (!(m->vl.skin > 0.0)) m->vl.skin = skin_default * m->r_max;
             int *ip = nullptr;
             const size_t n_int = Rm * S * (size_t)(2 + dm.Np + 32) / 32 * 32 + idx_bytes / sizeof(int);
             if (cudaMalloc(&ip, sizeof(int) * n_int) != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_NOMEM, "cudaMalloc failed"); }
@@ -523,7 +532,6 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
                 if (cudaMalloc(&pp, sizeof(unsigned short) * Rm * S * (size_t)dm.Np) != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_NOMEM, "cudaMalloc failed"); }
                 m->owned.push_back(pp); m->vl.perm = pp;
             }
-            { const char *vf = getenv("EHIC_VERLET_FUSED"); m->vl_fused = !(vf && !strcmp(vf, "0")); }
             const int vsm = (int)((sizeof(double) * 4 + sizeof(int)) * (size_t)dm.Np);
             cudaError_t ev = cudaFuncSetAttribute(verlet_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);
             if (ev == cudaSuccess) ev = cudaFuncSetAttribute(verlet_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);

@@ -13,7 +13,7 @@ rng = np.random.default_rng(0)
 X = np.stack([g["X"] + 0.01 * rng.normal(size=g["X"].shape) for _ in range(R)]).reshape(R, -1)
 t = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device=dev)
 x = t(X); p = t(rng.normal(size=X.shape)); norm = t(np.full(R, float(g["norm"])))
-lam = t(np.linspace(0.1, 1, R)); bet = t(np.linspace(0.1, 1, R)); eps = t(np.full(R, 1e-4)); H = torch.zeros(R, 4, dtype=torch.float64, device=dev)
+lam = t(np.linspace(0.1, 1, R)); bet = t(np.linspace(0.1, 1, R)); eps = t(np.full(R, float(os.environ.get("SB_EPS", 1e-4)))); H = torch.zeros(R, 4, dtype=torch.float64, device=dev)
 run = lambda: m.hmc_trajectory_device(R, L, x, p, norm, lam, bet, eps, H)
 run(); torch.cuda.synchronize()
 kt = m.kernel_times(run, repeats=3)

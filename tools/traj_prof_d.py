@@ -14,7 +14,7 @@ m = Model(S, np.full(N, 0.5), data, np.full(len(i), 1.25), alpha=10.0, k_nb=500.
 X = np.stack([random_walk(rng, S, N, 0.9) for _ in range(R)]).reshape(R, -1)
 t = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), device=dev)
 x = t(X); p = t(rng.normal(size=X.shape)); norm = t(np.full(R, 3.0))
-lam = t(np.linspace(0.1, 1, R)); bet = t(np.linspace(0.1, 1, R)); eps = t(np.full(R, 1e-4)); H = torch.zeros(R, 4, dtype=torch.float64, device=dev)
+lam = t(np.linspace(0.1, 1, R)); bet = t(np.linspace(0.1, 1, R)); eps = t(np.full(R, float(os.environ.get("SB_EPS", 1e-4)))); H = torch.zeros(R, 4, dtype=torch.float64, device=dev)
 run = lambda: m.hmc_trajectory_device(R, L, x, p, norm, lam, bet, eps, H)
 run(); torch.cuda.synchronize()
 kt = m.kernel_times(run, repeats=3)
