@@ -63,6 +63,7 @@ struct ehic_model {
     int n_quads = 0;                // lane path: backward CTAs per (replica, structure group)
     int n_quads_split = 0;          // the same with long rows cut into segments (few replicas per GPU)
     const int4 *lane_items_split = nullptr;
+    bool in_split = false;          // enqueueing one of two concurrent half batches: no replica-resident launches (they fill every SM)
     int last_lane_quads = 0;        // quads per (replica, structure group) of the last backward launch (kinetic partials)
     int lane_split_mode = -1;       // EHIC_LANE_SPLIT: 0 / 1 forced, -1 by launch size
     std::vector<long long> lane_item_work;  // host: CSR entries (+ epilogue) per backward work item
@@ -757,7 +758,7 @@ static int launch_forward(ehic_model *m, int R, const double *xs, const double *
     dim3 grid((unsigned)m->nA, (unsigned)R);
     if (m->use_lanes) {
         const long long nv = (long long)R * m->nA;
-        if (m->lane_res_fwd && nv >= 2LL * m->n_sm) {              // a replica's pairs on one SM: its lane copy stays in L1
+        if (m->lane_res_fwd && !m->in_split && nv >= 2LL * m->n_sm) {              // a replica's pairs on one SM: its lane copy stays in L1
             LaneSched sc{EHIC_LANE_FWD_GROUPS, nv, m->nA, nullptr};
             if (m->f32)
                 forward_lane32_resident_kernel<<<m->n_sm, EHIC_LANE_FWD_GROUPS * 256, 0, st>>>(
@@ -1332,12 +1333,16 @@ static int enqueue_trajectory(ehic_model_t *m, int R, int n_steps, double *d_x, 
                               const double *d_norm, const double *d_lammda, const double *d_beta,
                               const double *d_eps, double *d_H, cudaStream_t st)
 {
-    // automatic only on the dense tile path (FP64-bound kernels whose last waves are partial); on the sparse
-    // lane path, bound by L2 traffic, two concurrent halves were measured 5 % slower
+    // automatic on the dense tile path (FP64-bound kernels whose last waves are partial) ...
     const bool heavy = m->use_tiles && (double)m->dm.S * (double)m->dm.M * (R / 2) >= 2e8;
-    const int parts = m->opt_split >= 0 ? m->opt_split : (heavy ? 2 : 1);
+    // ... and on the lane path when the GPU holds FEW replicas (the ladder strong-scaled over several GPUs): every kernel
+    // of a step is then two or three partial waves, and two half batches running out of phase fill each other's tails
+    // (nora2012, 38 replicas: 192 -> 159 us per leapfrog step; 76: 332 -> 304; 151: 596 -> 571; 302: no difference)
+    const bool light = m->use_lanes && (long long)R * m->ld.nkg * m->n_quads < 16LL * 8 * std::max(m->n_sm, 1);
+    const int parts = m->opt_split >= 0 ? m->opt_split : ((heavy || light) ? 2 : 1);
     if (parts < 2 || R < 4 || m->profiling || st == m->st_stream2)
         return enqueue_trajectory_part(m, R, n_steps, d_x, d_p, d_norm, d_lammda, d_beta, d_eps, d_H, st);
+    struct SplitScope { ehic_model *m; SplitScope(ehic_model *m_) : m(m_) { m->in_split = true; } ~SplitScope() { m->in_split = false; } } split_scope(m);
     const int h = R / 2;
     const size_t per = (size_t)m->dm.S * m->dm.N * 3;
     CU(cudaEventRecord(m->ev_half, st));
