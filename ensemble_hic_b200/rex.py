@@ -200,6 +200,8 @@ class ReplicaExchange(object):
         rmax = int(np.max(np.diff(self.bounds)))
         pad = torch.zeros(rmax, width, dtype=local.dtype, device=local.device)
         pad[:self.R] = local
+        if pad.is_cuda and self.dist.get_backend() == "gloo":      # gloo gathers host tensors (tests: two ranks on one GPU)
+            pad = pad.cpu()
         out = [torch.empty_like(pad) for _ in range(self.world)]
         self.dist.all_gather(out, pad)
         rows = [out[r][:self.bounds[r + 1] - self.bounds[r]] for r in range(self.world)]
