@@ -533,7 +533,7 @@ int ehic_model_create(const ehic_model_desc_t *desc, int device, ehic_model_t **
                 if (cudaMalloc(&pp, sizeof(unsigned short) * Rm * S * (size_t)dm.Np) != cudaSuccess) { ehic_model_destroy(m); return fail(EHIC_ERR_NOMEM, "cudaMalloc failed"); }
                 m->owned.push_back(pp); m->vl.perm = pp;
             }
-            const int vsm = (int)((sizeof(double) * 4 + sizeof(int)) * (size_t)dm.Np);
+            const int vsm = (int)((sizeof(double) * 7 + sizeof(int)) * (size_t)dm.Np);
             cudaError_t ev = cudaFuncSetAttribute(verlet_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);
             if (ev == cudaSuccess) ev = cudaFuncSetAttribute(verlet_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);
             if (ev == cudaSuccess) ev = cudaFuncSetAttribute(verlet_step_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsm);
@@ -814,7 +814,7 @@ static int launch_prior(ehic_model *m, int R, int terms, const double *xs, const
         // one launch per step: displacement check, conditional list rebuild, list (or overflow all-pairs) force, backbone,
         // sphere and the energy sums of every structure (kernels.cuh: verlet_step_kernel)
         const unsigned n_struct = (unsigned)((long long)R * m->dm.S);
-        const size_t vsm = (sizeof(double) * 4 + sizeof(int)) * (size_t)m->dm.Np;
+        const size_t vsm = (sizeof(double) * 7 + sizeof(int)) * (size_t)m->dm.Np;
         double *pc = want_energy ? m->partC : nullptr;
         if (want_energy) CU(cudaMemsetAsync(m->partP, 0, sizeof(double) * 3 * (size_t)R * m->dm.S * m->nPx, st));   // nothing from prior_kernel
         const int N = m->dm.N;

@@ -1303,22 +1303,34 @@ gather_kernel(DevModel dm, GatherArgs ga, int nkt, int nktg)
 //      all-pairs from shared memory, which is what prior_kernel's fast path computes (same pairs, ascending order);
 //   3. evaluates the nonbonded force of every bead from its list, then the backbone and sphere terms (bonded_terms),
 //      writes the prior gradient once and, on request, the three energy sums of the structure.
-// A thread reads back only list rows it wrote itself, so no grid-wide ordering is needed.  Energies: thread <-> bead
-// is static, the block sum has a fixed order.
+// Lists are read back only by threads of the CTA that wrote them (after a CTA barrier), so no grid-wide ordering is
+// needed.  Determinism: a bead's force does not depend on which thread computes it; the energy terms go through a
+// per-bead shared-memory table and are summed in bead order, so H has the same bits in every run although the work
+// order (a counting sort by list length with shared-memory integer atomics) may differ between runs.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 8 : THREADS <= 256 ? 4 : THREADS <= 320 ? 3 : 2)
 verlet_step_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, const double *__restrict__ beta,
                    double *__restrict__ gprior, double *__restrict__ partC, int terms)
 {
-    extern __shared__ __align__(16) double vsm[];              // [Np] records (x, y, z, radius), then [Np] ints (list lengths)
+    extern __shared__ __align__(16) double vsm[];              // [Np] records (x, y, z, radius), [3][Np] energies, [Np] ints (list lengths)
     __shared__ double sh[3][THREADS / 32];
+    __shared__ int s_bin[EHIC_VL_CAP + 2];
     const long long rk = blockIdx.x;
     const int r = (int)(rk / dm.S);
     const int Np = dm.Np, N = dm.N, tid = threadIdx.x;
     const double *xk = xs + rk * 3LL * Np;
     double4 *sb = reinterpret_cast<double4 *>(vsm);
-    int *s_cnt = reinterpret_cast<int *>(vsm + 4 * Np);
+    double *s_e = vsm + 4 * Np;                                // [3][Np] per-bead energy terms (energy steps only)
+    int *s_cnt = reinterpret_cast<int *>(vsm + 7 * Np);
     int st = vl.state[rk];
+    int *cnt = vl.cnt + rk * Np;
+    unsigned short *idx = vl.idx + rk * (long long)Np * EHIC_VL_CAP;
+    unsigned short *perm = vl.perm + rk * Np;
+    // The kernel is bound by round trips to L2 (state -> coordinates -> work order -> list length and row: half of its
+    // stall samples, profiles/r02_nora_final_kernels_R302.txt), so the list of this thread's first bead is requested up
+    // front: the work order with the state, the length and the first 16 entries as soon as the bead is known, before the
+    // displacement check.  A rebuild in this step overwrites them; they are then read again.
+    int pre_b = min((int)perm[min(tid, N - 1)], N - 1);        // (never-built lists: any valid bead)
     double *xr = vl.xref + rk * 3LL * Np;
     double mx = 0.0;
     for (int b = tid; b < Np; b += THREADS) {
@@ -1330,12 +1342,12 @@ verlet_step_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, con
             mx = fmax(mx, (d == d) ? d : 1e300);               // NaN coordinates: rebuild (and let the sweep see them)
         }
     }
+    int pre_n = cnt[pre_b];
+    uint4 pre_w0 = reinterpret_cast<const uint4 *>(idx + (long long)pre_b * EHIC_VL_CAP)[0];
+    uint4 pre_w1 = reinterpret_cast<const uint4 *>(idx + (long long)pre_b * EHIC_VL_CAP)[1];
     const bool moved = mx > 0.25 * vl.skin * vl.skin;
     const bool stale = st == 0 || (st == 1 && __syncthreads_or(moved));      // st is CTA-uniform
     if (st != 1) __syncthreads();                                            // shared coordinates complete
-    int *cnt = vl.cnt + rk * Np;
-    unsigned short *idx = vl.idx + rk * (long long)Np * EHIC_VL_CAP;
-    unsigned short *perm = vl.perm + rk * Np;
     if (stale) {
         bool over = false;
         const double skin = vl.skin;
@@ -1361,19 +1373,37 @@ verlet_step_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, con
         st = __syncthreads_or(over) ? 2 : 1;                  // (also: s_cnt complete)
         if (tid == 0) vl.state[rk] = st;
         // work order of the force phase: beads sorted by list length, longest first (the lanes of a warp then walk lists of
-        // similar length: a warp costs its longest list).  Rank by counting -- deterministic, O(N^2) once per rebuild.
-        for (int b = tid; b < N; b += THREADS) {
-            const int c = s_cnt[b];
-            int rank = 0;
-            for (int o = 0; o < N; o++) { const int co = s_cnt[o]; rank += (co > c || (co == c && o < b)) ? 1 : 0; }
-            perm[rank] = (unsigned short)b;
+        // similar length: a warp costs its longest list).  Counting sort with integer shared-memory atomics: which of two
+        // beads with equal list lengths comes first depends on the scheduling, but no result does -- a bead's force does
+        // not depend on which thread computes it, and the energies are summed per bead in bead order (below).
+        for (int q = tid; q < EHIC_VL_CAP + 2; q += THREADS) s_bin[q] = 0;
+        __syncthreads();
+        for (int b = tid; b < N; b += THREADS) atomicAdd(&s_bin[EHIC_VL_CAP - s_cnt[b] + 1], 1);
+        __syncthreads();
+        if (tid < 32) {                                         // exclusive prefix over the 66 bins, three per lane
+            int v[3], sum = 0;
+#pragma unroll
+            for (int u = 0; u < 3; u++) { const int q = 3 * tid + u; v[u] = q < EHIC_VL_CAP + 2 ? s_bin[q] : 0; sum += v[u]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
+            int run = incl - sum;
+#pragma unroll
+            for (int u = 0; u < 3; u++) { const int q = 3 * tid + u; if (q < EHIC_VL_CAP + 2) s_bin[q] = run; run += v[u]; }
         }
+        __syncthreads();
+        for (int b = tid; b < N; b += THREADS) perm[atomicAdd(&s_bin[EHIC_VL_CAP - s_cnt[b] + 1], 1)] = (unsigned short)b;
         __syncthreads();                                        // perm is read by other threads below (same CTA)
+        pre_b = (int)perm[min(tid, N - 1)];
+        pre_n = cnt[pre_b];
+        pre_w0 = reinterpret_cast<const uint4 *>(idx + (long long)pre_b * EHIC_VL_CAP)[0];
+        pre_w1 = reinterpret_cast<const uint4 *>(idx + (long long)pre_b * EHIC_VL_CAP)[1];
     }
     const double sc = (beta ? beta[r] : 1.0) * (dm.k_nb * 2.0);
-    double e_nb = 0.0, e_bb = 0.0, e_sp = 0.0;
     for (int t = tid; t < N; t += THREADS) {
-        const int b = st == 2 ? t : (int)perm[t];
+        double e_nb = 0.0, e_bb = 0.0, e_sp = 0.0;
+        const bool first = t == tid;
+        const int b = st == 2 ? t : (first ? pre_b : (int)perm[t]);
         const double4 me = sb[b];
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
         auto visit = [&](int o, bool live) {
@@ -1394,10 +1424,10 @@ verlet_step_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, con
             for (int o = 0; o < N; o++) visit(o == b ? (b + 1 < N ? b + 1 : b - 1) : o, o != b);
         } else {
             // ascending partner order, as in prior_kernel; the list of a bead is one 128-byte line, 8 indices per load
-            const int n = cnt[b];
+            const int n = first ? pre_n : cnt[b];
             const uint4 *row = reinterpret_cast<const uint4 *>(idx + (long long)b * EHIC_VL_CAP);
             for (int u0 = 0; u0 < n; u0 += 8) {
-                const uint4 w = row[u0 >> 3];
+                const uint4 w = (first && u0 == 0) ? pre_w0 : ((first && u0 == 8) ? pre_w1 : row[u0 >> 3]);
                 const unsigned ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
@@ -1413,8 +1443,12 @@ verlet_step_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, con
             double *o = gprior + (rk * N + b) * 3;
             o[0] = g0; o[1] = g1; o[2] = g2;
         }
+        if (partC) { s_e[b] = e_nb; s_e[Np + b] = e_bb; s_e[2 * Np + b] = e_sp; }
     }
     if (partC) {
+        __syncthreads();
+        double e_nb = 0.0, e_bb = 0.0, e_sp = 0.0;             // bead order, whatever the work order was
+        for (int b = tid; b < N; b += THREADS) { e_nb += s_e[b]; e_bb += s_e[Np + b]; e_sp += s_e[2 * Np + b]; }
         e_nb = warp_sum(e_nb); e_bb = warp_sum(e_bb); e_sp = warp_sum(e_sp);
         if ((tid & 31) == 0) { sh[0][tid >> 5] = e_nb; sh[1][tid >> 5] = e_bb; sh[2][tid >> 5] = e_sp; }
         __syncthreads();
