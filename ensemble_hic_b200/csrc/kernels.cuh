@@ -1349,17 +1349,29 @@ verlet_step_kernel(DevModel dm, VerletDev vl, const double *__restrict__ xs, con
     const bool stale = st == 0 || (st == 1 && __syncthreads_or(moved));      // st is CTA-uniform
     if (st != 1) __syncthreads();                                            // shared coordinates complete
     if (stale) {
+        // The membership test runs on the FP32 pipe (the N^2 tests of a rebuild cost several normal steps).  A list only has
+        // to be a SUPERSET of the pairs within r_i + r_j + skin: every radius is inflated by a bound on the rounding error
+        // of the bead's float coordinates (2.5e-7 |x|_1, four times the worst case), so no pair inside the FP64 range is
+        // missed; the few extra members contribute exact zeros in the force phase, whose own test stays FP64.
         bool over = false;
-        const double skin = vl.skin;
+        float4 *sf = reinterpret_cast<float4 *>(s_e);            // the energy table is free until the end of the step
         for (int b = tid; b < N; b += THREADS) {
             const double4 me = sb[b];
+            const float fx = (float)me.x, fy = (float)me.y, fz = (float)me.z;
+            sf[b] = make_float4(fx, fy, fz, (float)me.w * 1.000001f + 2.5e-7f * (fabsf(fx) + fabsf(fy) + fabsf(fz)));
+        }
+        __syncthreads();
+        const float skin = (float)vl.skin * 1.000001f + 1e-6f;
+        for (int b = tid; b < N; b += THREADS) {
+            const double4 me = sb[b];
+            const float4 mf = sf[b];
             unsigned short *row = idx + (long long)b * EHIC_VL_CAP;
             int n = 0;
             for (int o = 0; o < N; o++) {
-                const double4 p = sb[o];
-                const double dx = p.x - me.x, dy = p.y - me.y, dz = p.z - me.z;
-                const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                const double lim = me.w + p.w + skin;
+                const float4 p = sf[o];
+                const float dx = p.x - mf.x, dy = p.y - mf.y, dz = p.z - mf.z;
+                const float s2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                const float lim = mf.w + p.w + skin;
                 if (!(s2 >= lim * lim) && o != b) {             // !(>=): NaN distances are listed, like the sweep would see them
                     if (n < EHIC_VL_CAP) row[n] = (unsigned short)o;
                     n++;
