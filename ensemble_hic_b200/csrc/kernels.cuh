@@ -1639,7 +1639,9 @@ forward_lane_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, cons
     forward_lane_body(dm, ld, xg, norm, md_out, wbuf, partA, want_logl, blockIdx.x, blockIdx.y, threadIdx.x, 0, sh);
 }
 
+#ifndef EHIC_LANE_FWD_GROUPS
 #define EHIC_LANE_FWD_GROUPS 3                   // resident launch: 3 x 256 threads per SM
+#endif
 __global__ void __launch_bounds__(EHIC_LANE_FWD_GROUPS * 256, 1)
 forward_lane_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, const double *__restrict__ xg, const double *__restrict__ norm,
                              double *__restrict__ md_out, double *__restrict__ wbuf,
