@@ -1553,7 +1553,8 @@ __device__ __forceinline__ void lane_resident_range(const LaneSched &sc, long lo
 __device__ __forceinline__ void
 forward_lane_body(const DevModel &dm, const LaneDev &ld, const double *__restrict__ xg, const double *__restrict__ norm,
                   double *__restrict__ md_out, double *__restrict__ wbuf,
-                  double *__restrict__ partA, int want_logl, int vblock, int r, int tid, int group, double *sh /* [8] */)
+                  double *__restrict__ partA, int want_logl, int vblock, int r, int tid, int group, double *sh /* [8] */,
+                  int4 *stage /* [256] */)
 {
     const int lane = tid & 31, warp = tid >> 5;
     const long long m0 = ((long long)vblock * 8 + warp) * 32;
@@ -1562,6 +1563,11 @@ forward_lane_body(const DevModel &dm, const LaneDev &ld, const double *__restric
     const double *xr = xg + (long long)r * ld.nkg * gstride + lane;
     double term = 0.0;
     if (m0 < dm.M) {                                    // warp-uniform
+        // the warp's 32 pair records: one coalesced load, parked in the warp's shared-memory slot, read back as broadcasts
+        int4 *se = stage + warp * 32;
+        __syncwarp();
+        se[lane] = __ldg(reinterpret_cast<const int4 *>(ld.pairs + min(m0 + lane, dm.M - 1)));
+        __syncwarp();
         double tot[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int b = 0; b < 4; b++) {
@@ -1570,32 +1576,45 @@ forward_lane_body(const DevModel &dm, const LaneDev &ld, const double *__restric
                 double acc[8];
 #pragma unroll
                 for (int e = 0; e < 8; e++) acc[e] = 0.0;
+                const int i_first = se[b * 8].x;
+                const bool one_row = i_first == se[b * 8 + 7].x;      // sorted by (i, j): the 8 pairs share bead i (the usual case)
                 for (int kg = 0; kg < ld.nkg; kg++) {
                     const double *xk = xr + kg * gstride;
                     const bool kv = kg * 32 + lane < dm.S;
-                    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-                    int ci = -1;
-                    LanePair pr[8];                     // re-read per structure group (L1-resident broadcast loads)
+                    const double *p0 = xk + (long long)i_first * 96;
+                    double a0 = p0[0], a1 = p0[32], a2 = p0[64];
+                    if (one_row) {
 #pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        const int4 v = __ldg(reinterpret_cast<const int4 *>(ld.pairs + min(mb + e, dm.M - 1)));
-                        pr[e].i = v.x; pr[e].j = v.y; pr[e].dc = __hiloint2double(v.w, v.z);
-                    }
-#pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        if (pr[e].i != ci) {            // warp-uniform
-                            ci = pr[e].i;
-                            const double *p = xk + (long long)ci * 96;
-                            a0 = p[0]; a1 = p[32]; a2 = p[64];
+                        for (int e = 0; e < 8; e++) {
+                            const int4 v = se[b * 8 + e];
+                            const double *q = xk + (long long)v.y * 96;
+                            const double dx = a0 - q[0], dy = a1 - q[32], dz = a2 - q[64];
+                            const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                            const double rd = rsqrt_nr(s2);
+                            const double tt = alpha * (__hiloint2double(v.w, v.z) - s2 * rd);
+                            const double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                            const double sv = fma(tt, rq, 1.0);
+                            acc[e] += kv ? sv : 0.0;
                         }
-                        const double *q = xk + (long long)pr[e].j * 96;
-                        const double dx = a0 - q[0], dy = a1 - q[32], dz = a2 - q[64];
-                        const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                        const double rd = rsqrt_nr(s2);
-                        const double tt = alpha * (pr[e].dc - s2 * rd);
-                        const double rq = rsqrt_nr(fma(tt, tt, 1.0));
-                        const double sv = fma(tt, rq, 1.0);
-                        acc[e] += kv ? sv : 0.0;
+                    } else {
+                        int ci = i_first;
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            const int4 v = se[b * 8 + e];
+                            if (v.x != ci) {            // warp-uniform
+                                ci = v.x;
+                                const double *p = xk + (long long)ci * 96;
+                                a0 = p[0]; a1 = p[32]; a2 = p[64];
+                            }
+                            const double *q = xk + (long long)v.y * 96;
+                            const double dx = a0 - q[0], dy = a1 - q[32], dz = a2 - q[64];
+                            const double s2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                            const double rd = rsqrt_nr(s2);
+                            const double tt = alpha * (__hiloint2double(v.w, v.z) - s2 * rd);
+                            const double rq = rsqrt_nr(fma(tt, tt, 1.0));
+                            const double sv = fma(tt, rq, 1.0);
+                            acc[e] += kv ? sv : 0.0;
+                        }
                     }
                 }
                 reduce8(acc, lane);                     // lane L holds the total of pair mb + (L >> 2)
@@ -1636,7 +1655,8 @@ forward_lane_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, cons
                     double *__restrict__ partA, int want_logl)
 {
     __shared__ double sh[8];
-    forward_lane_body(dm, ld, xg, norm, md_out, wbuf, partA, want_logl, blockIdx.x, blockIdx.y, threadIdx.x, 0, sh);
+    __shared__ int4 stage[256];
+    forward_lane_body(dm, ld, xg, norm, md_out, wbuf, partA, want_logl, blockIdx.x, blockIdx.y, threadIdx.x, 0, sh, stage);
 }
 
 #ifndef EHIC_LANE_FWD_GROUPS
@@ -1648,12 +1668,13 @@ forward_lane_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, const double
                              double *__restrict__ partA, int want_logl)
 {
     __shared__ double sh[EHIC_LANE_FWD_GROUPS][8];
+    __shared__ int4 stage[EHIC_LANE_FWD_GROUPS][256];
     const int group = threadIdx.x >> 8, tid = threadIdx.x & 255;
     long long v0, v1;
     lane_resident_range(sc, v0, v1);
     for (long long v = v0 + group; v < v1; v += EHIC_LANE_FWD_GROUPS) {
         const int r = (int)(v / sc.per_replica), vb = (int)(v - (long long)r * sc.per_replica);
-        forward_lane_body(dm, ld, xg, norm, md_out, wbuf, partA, want_logl, vb, r, tid, group, sh[group]);
+        forward_lane_body(dm, ld, xg, norm, md_out, wbuf, partA, want_logl, vb, r, tid, group, sh[group], stage[group]);
     }
 }
 
@@ -2546,7 +2567,8 @@ backward_tile32_kernel(DevModel dm, TileDev td, BackwardTile32Args ba)
 __device__ __forceinline__ void
 forward_lane32_body(const DevModel &dm, const LaneDev &ld, const double *__restrict__ xg, const double *__restrict__ norm,
                     double *__restrict__ md_out, float *__restrict__ wbuf32,
-                    double *__restrict__ partA, int want_logl, int vblock, int r, int tid, int group, double *sh /* [8] */)
+                    double *__restrict__ partA, int want_logl, int vblock, int r, int tid, int group, double *sh /* [8] */,
+                    int4 *stage /* [256] */)
 {
     const int lane = tid & 31, warp = tid >> 5;
     const long long m0 = ((long long)vblock * 8 + warp) * 32;
@@ -2556,6 +2578,11 @@ forward_lane32_body(const DevModel &dm, const LaneDev &ld, const double *__restr
     const float2 *xr = reinterpret_cast<const float2 *>(xg) + (long long)r * ld.nkg * gstride + lane;
     double term = 0.0;
     if (m0 < dm.M) {                                    // warp-uniform
+        // the warp's 32 pair records through its shared-memory slot, as in forward_lane_body
+        int4 *se = stage + warp * 32;
+        __syncwarp();
+        se[lane] = __ldg(reinterpret_cast<const int4 *>(ld.pairs32 + min(m0 + lane, dm.M - 1)));
+        __syncwarp();
         float tot[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int b = 0; b < 4; b++) {
@@ -2564,29 +2591,29 @@ forward_lane32_body(const DevModel &dm, const LaneDev &ld, const double *__restr
                 float acc[8];
 #pragma unroll
                 for (int e = 0; e < 8; e++) acc[e] = 0.f;
+                const int i_first = se[b * 8].x;
                 for (int kg = 0; kg < ld.nkg; kg++) {
                     const float2 *xk = xr + kg * gstride;
                     const bool kv = kg * 32 + lane < dm.S;
-                    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
-                    int ci = -1;
-                    int4 pr[8];                         // (i, j, dc, -): re-read per structure group (L1-resident broadcast loads)
-#pragma unroll
-                    for (int e = 0; e < 8; e++) pr[e] = __ldg(reinterpret_cast<const int4 *>(ld.pairs32 + min(mb + e, dm.M - 1)));
+                    const float2 *p0 = xk + (long long)i_first * 96;
+                    float2 a0 = p0[0], a1 = p0[32], a2 = p0[64];
+                    int ci = i_first;
 #pragma unroll
                     for (int e = 0; e < 8; e++) {
-                        if (pr[e].x != ci) {            // warp-uniform
-                            ci = pr[e].x;
+                        const int4 v = se[b * 8 + e];
+                        if (v.x != ci) {                // warp-uniform, rare: the pairs are sorted by (i, j)
+                            ci = v.x;
                             const float2 *p = xk + (long long)ci * 96;
                             a0 = p[0]; a1 = p[32]; a2 = p[64];
                         }
-                        const float2 *q = xk + (long long)pr[e].y * 96;
+                        const float2 *q = xk + (long long)v.y * 96;
                         const float2 q0 = q[0], q1 = q[32], q2 = q[64];
                         const float dx = (a0.x - q0.x) + (a0.y - q0.y);
                         const float dy = (a1.x - q1.x) + (a1.y - q1.y);
                         const float dz = (a2.x - q2.x) + (a2.y - q2.y);
                         const float s2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                         const float rd = rsqrt_f32(s2);
-                        const float tt = alpha * (__int_as_float(pr[e].z) - s2 * rd);
+                        const float tt = alpha * (__int_as_float(v.z) - s2 * rd);
                         const float rq = rsqrt_f32_raw(fmaf(tt, tt, 1.0f));
                         const float a = fabsf(tt) * rq;      // |t| / q in [0, 1)
                         const float den = 1.0f + a;
@@ -2632,7 +2659,8 @@ forward_lane32_kernel(DevModel dm, LaneDev ld, const double *__restrict__ xg, co
                       double *__restrict__ partA, int want_logl)
 {
     __shared__ double sh[8];
-    forward_lane32_body(dm, ld, xg, norm, md_out, wbuf32, partA, want_logl, blockIdx.x, blockIdx.y, threadIdx.x, 0, sh);
+    __shared__ int4 stage[256];
+    forward_lane32_body(dm, ld, xg, norm, md_out, wbuf32, partA, want_logl, blockIdx.x, blockIdx.y, threadIdx.x, 0, sh, stage);
 }
 
 __global__ void __launch_bounds__(EHIC_LANE_FWD_GROUPS * 256, 1)
@@ -2641,12 +2669,13 @@ forward_lane32_resident_kernel(DevModel dm, LaneDev ld, LaneSched sc, const doub
                                double *__restrict__ partA, int want_logl)
 {
     __shared__ double sh[EHIC_LANE_FWD_GROUPS][8];
+    __shared__ int4 stage[EHIC_LANE_FWD_GROUPS][256];
     const int group = threadIdx.x >> 8, tid = threadIdx.x & 255;
     long long v0, v1;
     lane_resident_range(sc, v0, v1);
     for (long long v = v0 + group; v < v1; v += EHIC_LANE_FWD_GROUPS) {
         const int r = (int)(v / sc.per_replica), vb = (int)(v - (long long)r * sc.per_replica);
-        forward_lane32_body(dm, ld, xg, norm, md_out, wbuf32, partA, want_logl, vb, r, tid, group, sh[group]);
+        forward_lane32_body(dm, ld, xg, norm, md_out, wbuf32, partA, want_logl, vb, r, tid, group, sh[group], stage[group]);
     }
 }
 
