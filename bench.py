@@ -728,6 +728,11 @@ def run_b200(args):
                     "note": "per step of the whole resident batch: when the batch runs as several part launches, achieved = "
                             "algorithmic flop of the batch / summed duration of the kernel's launches, traffic = sum over them",
                     "kernel_ms": kern,
+                    "issue_ceiling": ({"frac": FLOP_BWD_PER_PAIR / (2.0 * 29.84),
+                                       "note": "backward_tile_kernel issues 29 FP64 instructions + 0.84 reduction adds per (structure, "
+                                               "data point) for 23 algorithmic flop and the peak counts an FMA as 2 flop: frac cannot "
+                                               "exceed this value (DESIGN.md 6.1); frac / ceiling = share of the FP64 issue slots used"}
+                                      if tiles else None),
                     "step": {"achieved": flop_step / (ms / args.steps * 1e-3) / 1e12, "peak": fp64_tf,
                              "frac": flop_step / (ms / args.steps * 1e-3) / 1e12 / fp64_tf,
                              "algorithmic_flop_per_step": flop_step},
