@@ -14,10 +14,12 @@
  *     reference's known-answer tests (tests/cases/forward_models.py,
  *     tests/cases/backbone_prior.py) in tests/test_oracle.py;
  *   - the neighbour list + PROLSQ part restates ensemble_hic/c/{nblist,forcefield,
- *     prolsq,mathutils}.c, which is a Python-2 C-API extension that does not build
- *     against CPython 3; the reference has no test for it ("parity unpinned" by
- *     reference fixtures).  It is cross-checked against the compilable O(N^2)
- *     forcefield_c.pyx, which is algebraically identical for d0 = r_i + r_j.
+ *     prolsq,mathutils}.c.  Those sources are a Python-2 C-API extension that does not
+ *     build as an extension of CPython 3, but oracle/build_ref.build_nbl compiles them
+ *     UNMODIFIED as plain C against the stand-in headers in oracle/shim/ (oracle/_ref/
+ *     libref_nbl.so, interface oracle/ref_nbl_driver.c); this restatement equals them bit
+ *     for bit -- same contacts in the same list order, same energy and gradient bits --
+ *     and reproduces the golden vectors generated from them (tests/golden/nbl_reference.npz).
  */
 #include <math.h>
 #include <stdint.h>

@@ -16,7 +16,8 @@ Two layers:
   nonbonded_prior.py:103-121,158-164).
 
 :func:`load_ref` imports the reference's own compiled Cython modules from
-``oracle/_ref`` (built by ``oracle/build_ref.py``) when present.
+``oracle/_ref`` (built by ``oracle/build_ref.py``) when present; :class:`RefNBL` loads the
+reference's own neighbour-list / PROLSQ C sources compiled as plain C (``build_ref.build_nbl``).
 
 The HMC restatement (:func:`leapfrog`, :func:`hmc_step`) follows csb 1.2.5's
 ``FastLeapFrog`` / binf's ``HMCSampler`` as recalled from their public sources; those
@@ -221,6 +222,58 @@ class OracleNBLForceField(object):
         self.co.L.oracle_nbl_gradient(self.nbl.h, _p(c), _p(forces), _p(self.bead_radii),
                                       self.force_constant, len(c), None)
         return forces.ravel()
+
+
+class RefNBL(object):
+    """The REFERENCE'S OWN neighbour list + PROLSQ forcefield (c/nblist.c, c/forcefield.c, c/prolsq.c compiled unmodified
+    into oracle/_ref/libref_nbl.so by oracle/build_ref.build_nbl; interface: oracle/ref_nbl_driver.c).  Used only to pin
+    OracleNBList / OracleNBLForceField.  ``RefNBL.load()`` returns None when the library has not been built.
+    Atom types are 0..n-1 as the reference intends (its int64 -> int aliasing of ``types``, SURVEY quirk B-1, is a property
+    of the numpy buffer it is handed, not of this C code)."""
+
+    @staticmethod
+    def load():
+        path = os.path.join(HERE, "_ref", "libref_nbl.so")
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        vp = C.c_void_p
+        L.ref_nblist_new.restype = vp; L.ref_nblist_new.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int]
+        L.ref_nblist_free.argtypes = [vp]
+        L.ref_nblist_update.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.ref_nblist_pairs.argtypes = [vp, vp, C.c_int]
+        L.ref_nblff_new.restype = vp; L.ref_nblff_new.argtypes = [C.c_int, vp, C.c_double]
+        L.ref_nblff_free.argtypes = [vp]
+        L.ref_nblff_energy.restype = C.c_double; L.ref_nblff_energy.argtypes = [vp, vp]
+        L.ref_nblff_gradient.restype = C.c_double; L.ref_nblff_gradient.argtypes = [vp, vp, vp]
+        return RefNBL(L)
+
+    def __init__(self, L):
+        self.L = L
+
+    def pairs(self, coords, cellsize, n_cells, n_per_cell):
+        """(total contacts, half list in the reference's list order) of NBList(cellsize, n_cells, n_per_cell, n).update(coords, 1)"""
+        c = _d(coords).reshape(-1, 3)
+        h = self.L.ref_nblist_new(float(cellsize), int(n_cells), int(n_per_cell), len(c))
+        try:
+            tot = self.L.ref_nblist_update(h, c.ctypes.data, len(c), 1)
+            out = np.empty((max(tot, 1), 2), dtype=np.int32)
+            self.L.ref_nblist_pairs(h, out.ctypes.data, tot)
+            return tot, out[:tot]
+        finally:
+            self.L.ref_nblist_free(h)
+
+    def energy_gradient(self, coords, bead_radii, force_constant):
+        """NBLForceField(bead_radii, k): (energy, gradient, energy accumulated by the gradient pass)"""
+        c = _d(coords).reshape(-1, 3); r = _d(bead_radii)
+        h = self.L.ref_nblff_new(len(c), r.ctypes.data, float(force_constant))
+        try:
+            E = self.L.ref_nblff_energy(h, c.ctypes.data)
+            F = np.zeros(c.shape)
+            Eg = self.L.ref_nblff_gradient(h, c.ctypes.data, F.ctypes.data)
+            return E, F.ravel(), Eg
+        finally:
+            self.L.ref_nblff_free(h)
 
 
 # --------------------------------------------------------------------------------------

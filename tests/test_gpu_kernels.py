@@ -92,6 +92,24 @@ def test_nonbonded_matches_neighbour_list_path(co):
     assert abs(out["energies"][0, 1] - ref_E) <= 1e-12 * abs(ref_E)
 
 
+@pytest.mark.parametrize("exact", [False, True])
+def test_nonbonded_against_the_reference_c_golden_vectors(exact):
+    """tests/golden/nbl_reference.npz holds what the reference's OWN c/nblist.c + c/forcefield.c + c/prolsq.c return on
+    seeded structures (make_golden_nbl.py): uniform and mixed radii, a compact globule, a chain far from the origin, a
+    nora2012 structure.  The CUDA nonbonded term against those numbers directly"""
+    import os
+    from ensemble_hic_b200.engine import Model, TERM_NONBONDED
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nbl_reference.npz"))
+    for name in g["names"]:
+        x, radii, k = g[name + "_x"], g[name + "_radii"], float(g[name + "_k"])
+        m = Model(1, radii, k_nb=k, exact=exact)
+        out = m.evaluate(x.reshape(1, -1), 1.0, terms=TERM_NONBONDED, energies=True)
+        E, G = float(g[name + "_energy"]), g[name + "_gradient"]
+        assert relerr(out["grad"][0], G) < (1e-13 if exact else FAST_TOL), name
+        assert abs(out["energies"][0, 1] - E) <= 1e-12 * abs(E), name
+        m.close()
+
+
 @pytest.mark.parametrize("exact", [True, False])
 def test_backbone_gradient_bitexact_and_energy(co, exact):
     from oracle.oracle import backbone_log_prob_single

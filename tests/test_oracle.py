@@ -148,3 +148,54 @@ def test_neighbour_list_edge_cases(co):
     assert np.array_equal(nb.canonical_pairs(), [[0, 1], [2, 3]])
     one = OracleNBList(co, 1.001, 90, 1, 1)
     assert one.update(np.zeros((1, 3)), 1) == 0
+
+
+# ---- neighbour list + PROLSQ against the reference's own C (c/nblist.c, c/forcefield.c, c/prolsq.c) ------------------
+
+@pytest.fixture(scope="module")
+def ref_nbl():
+    """the reference's neighbour-list / PROLSQ C sources compiled as plain C (oracle/_ref/libref_nbl.so; travels with the tree)"""
+    from oracle import build_ref
+    from oracle.oracle import RefNBL
+    build_ref.build_nbl(verbose=False)        # no-op without /root/reference
+    r = RefNBL.load()
+    if r is None:
+        pytest.skip("oracle/_ref/libref_nbl.so not built (no /root/reference here)")
+    return r
+
+
+@pytest.mark.parametrize("seed,N,uniform,step", [(0, 50, True, 0.8), (1, 300, True, 0.8), (2, 300, False, 0.9), (3, 1000, False, 0.7),
+                                                  (4, 64, True, 0.3)])
+def test_c_oracle_neighbour_list_equals_reference_c_bit_for_bit(co, ref_nbl, seed, N, uniform, step):
+    """c/nblist.c:112-303 + c/forcefield.c:8-109 + c/prolsq.c:8-38, compiled unmodified, against the restatement in
+    ehic_oracle.c: the same contacts in the same list order, the same energy and gradient bits"""
+    from oracle.oracle import OracleNBList, OracleNBLForceField
+    from helpers import random_walk
+    rng = np.random.default_rng(seed)
+    radii = np.full(N, 0.5) if uniform else rng.uniform(0.35, 0.65, N)
+    x = np.ascontiguousarray(random_walk(rng, 1, N, step)[0])
+    cell = float(np.add.outer(radii, radii).max() + 1e-3)
+    tot, pairs = ref_nbl.pairs(x, cell, 90, N)
+    o = OracleNBList(co, cell, 90, N, N)
+    assert o.update(x, 1) == tot
+    assert np.array_equal(o.pairs(), pairs)
+    E, F, Eg = ref_nbl.energy_gradient(x, radii, 11.4)
+    ff = OracleNBLForceField(co, radii, 11.4)
+    assert ff.energy(x) == E
+    assert np.array_equal(ff.gradient(x), F)
+
+
+def test_c_oracle_neighbour_list_reproduces_the_reference_c_golden_vectors(co):
+    """tests/golden/nbl_reference.npz (tests/golden/make_golden_nbl.py: outputs of the reference's own C code) -- runs
+    wherever the repository is, with or without /root/reference"""
+    from oracle.oracle import OracleNBList, OracleNBLForceField
+    g = np.load(os.path.join(GOLD, "nbl_reference.npz"))
+    assert len(g["names"]) == 5
+    for name in g["names"]:
+        x, radii, k = g[name + "_x"], g[name + "_radii"], float(g[name + "_k"])
+        o = OracleNBList(co, float(g[name + "_cell"]), 90, len(x), len(x))
+        assert o.update(x, 1) == int(g[name + "_total"]), name
+        assert np.array_equal(o.pairs(), g[name + "_pairs"]), name
+        ff = OracleNBLForceField(co, radii, k)
+        assert ff.energy(x) == float(g[name + "_energy"]), name
+        assert np.array_equal(ff.gradient(x), g[name + "_gradient"]), name
