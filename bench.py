@@ -22,9 +22,9 @@ reference's CPU kernels timed beside it):
             per GPU: posterior gradient evaluations/s, weak scaling
 
 ``--impl reference`` times the reference's own CPU kernels (oracle/_ref: the unmodified
-Cython of /root/reference compiled for CPython 3; the neighbour-list forcefield through the
-plain-C restatement because the reference's Python-2 C extension cannot be built) on a
-bounded sample of the same workload with all host cores.
+Cython of /root/reference compiled for CPython 3, and its neighbour-list / PROLSQ C sources
+compiled unmodified as plain C, oracle/build_ref.build_nbl) on a bounded sample of the same
+workload with all host cores.
 """
 import argparse
 import json
@@ -166,6 +166,7 @@ def cpu_reference_rate(budget_s=20.0, cores=None):
     from oracle.oracle import build_c_oracle, load_ref
     build_c_oracle()
     build_ref.build(verbose=False)
+    build_ref.build_nbl(verbose=False)
     kind = "reference" if load_ref() is not None else "port"
     cores = cores or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
     try:
@@ -188,7 +189,9 @@ def cpu_reference_rate(budget_s=20.0, cores=None):
               "(cost linear in S, scaled by %d/%d); %d worker processes; %s kernels%s"
               % (N_BEADS, len(np.triu_indices(N_BEADS, 2)[0]), S_sample, N_STRUCT, N_STRUCT, S_sample, cores,
                  "reference Cython (oracle/_ref)" if kind == "reference" else "C oracle port",
-                 ", neighbour-list forcefield via C restatement"))
+                 ", neighbour-list forcefield: the reference's own c/nblist.c + c/prolsq.c (oracle/_ref/libref_nbl.so)"
+                 if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_nbl.so")) and kind == "reference"
+                 else ", neighbour-list forcefield via the bit-identical C restatement"))
     return rate, cores, kind, sample, wall
 
 
@@ -430,7 +433,7 @@ def bench_ladder(name, ctx, n_iter, L=100, swap_interval=5):
             out["cpu_baseline"] = {"value": tot / per_sweep, "unit": "RE sweeps/s (whole ladder)", "cores": cores,
                                    "kind": ctx["cpu_kind"], "replica_grad_evals_per_s": tot,
                                    "sample": "posterior gradients of one replica per core for 4 s (reference call sequence, "
-                                             "SURVEY 3.4; neighbour-list forcefield via the C restatement), converted with "
+                                             "SURVEY 3.4; neighbour-list forcefield: the reference's own C where oracle/_ref/libref_nbl.so exists, else its bit-identical restatement), converted with "
                                              "%.0f gradients per sweep of the ladder; energies, norm draw and exchange not "
                                              "charged to the CPU" % per_sweep}
         del xw, pw

@@ -276,6 +276,33 @@ class RefNBL(object):
             self.L.ref_nblff_free(h)
 
 
+class RefNBLForceField(object):
+    """NBLForceField (forcefields.py:152-224) on the reference's own C objects: one neighbour list + PROLSQ forcefield kept
+    for the lifetime of the object, the list rebuilt by every energy() and every gradient() as the reference does."""
+
+    def __init__(self, ref, bead_radii, force_constant):
+        self.L = ref.L
+        self.radii = _d(bead_radii)
+        self.n = len(self.radii)
+        self.h = self.L.ref_nblff_new(self.n, self.radii.ctypes.data, float(force_constant))
+        if not self.h:
+            raise MemoryError("reference forcefield allocation failed")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_nblff_free(self.h); self.h = None
+
+    def energy(self, structure):
+        c = _d(structure).reshape(-1, 3)
+        return self.L.ref_nblff_energy(self.h, c.ctypes.data)
+
+    def gradient(self, structure):
+        c = _d(structure).reshape(-1, 3)
+        forces = np.zeros(c.shape)
+        self.L.ref_nblff_gradient(self.h, c.ctypes.data, forces.ctypes.data)
+        return forces.ravel()
+
+
 # --------------------------------------------------------------------------------------
 # numpy restatements of the log-probabilities (the reference evaluates these in numpy)
 
@@ -310,9 +337,10 @@ class OraclePosterior(object):
     """The posterior assembled by setup_functions.make_posterior (setup_functions.py:64-98),
     evaluated with the reference's own arithmetic.  ``kernels`` is either a
     :class:`COracle` or the dict returned by :func:`load_ref` (the reference's compiled
-    Cython); the neighbour-list forcefield is always the C restatement (the reference's
-    C extension does not build on CPython 3) unless ``nonbonded='n2'`` selects the
-    compilable O(N^2) forcefield_c path."""
+    Cython).  The neighbour-list forcefield (``nonbonded='nbl'``, the production path) is the
+    reference's own C (:class:`RefNBLForceField`) when ``kernels`` is the reference and
+    oracle/_ref/libref_nbl.so has been built, else the bit-identical C restatement;
+    ``nonbonded='n2'`` selects the O(N^2) forcefield_c path.  ``nbl_kind`` says which."""
 
     def __init__(self, n_structures, data_points, contact_distances, alpha, bead_radii,
                  k_nb, k_bb, bb_ll, bb_ul, mol_ranges, sphere=None, gamma=None,
@@ -342,7 +370,13 @@ class OraclePosterior(object):
             self.ffE = k.forcefield_energy; self.ffG = k.forcefield_gradient
             self.bbG = k.backbone_prior_gradient; self.spG = k.sphere_prior_gradient
         self.nonbonded = nonbonded
-        self.nbl_ff = OracleNBLForceField(self.co, self.radii, self.k_nb) if nonbonded == "nbl" else None
+        self.nbl_ff, self.nbl_kind = None, None
+        if nonbonded == "nbl":
+            ref_nbl = RefNBL.load() if isinstance(k, dict) else None
+            if ref_nbl is not None:
+                self.nbl_ff, self.nbl_kind = RefNBLForceField(ref_nbl, self.radii, self.k_nb), "reference C (oracle/_ref/libref_nbl.so)"
+            else:
+                self.nbl_ff, self.nbl_kind = OracleNBLForceField(self.co, self.radii, self.k_nb), "C restatement"
 
     # ---- pieces -------------------------------------------------------------------
     def mock_data(self, x, norm):
