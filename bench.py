@@ -509,8 +509,8 @@ def bench_e(ctx, steps):
             out["cpu_baseline"] = {"value": use / wall, "unit": UNIT, "cores": use, "kind": ctx["cpu_kind"],
                                    "sample": "one posterior gradient per core at N=%d with S_sample=%d of %d structures and "
                                              "M_sample=%d of %d data points (contact term scaled by S/S_sample x M/M_sample, priors by "
-                                             "S/S_sample); reference call sequence; neighbour-list forcefield via the C "
-                                             "restatement" % (N, S_s, S, M_s, M)}
+                                             "S/S_sample); reference call sequence; neighbour-list forcefield: the reference's own C where "
+                                             "oracle/_ref/libref_nbl.so exists, else its bit-identical restatement" % (N, S_s, S, M_s, M)}
     m.close()
     del x, g
     torch.cuda.empty_cache()
